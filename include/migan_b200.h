@@ -1,0 +1,107 @@
+/* migan_b200.h -- C ABI of the B200-native MI-GAN generator forward.
+ *
+ * The shared library (mi-gan_b200/lib/libmigan_b200.so, built by __graft_entry__.build())
+ * exports exactly the entry points declared here: plain pointers and sizes, no torch types.
+ * Each one replaces a reference interface, cited as file:line in /root/reference:
+ *
+ *   migan_create / migan_destroy      Generator.__init__            lib/model_zoo/migan_inference.py:355-360
+ *   migan_set_weight / _finalize      nn.Module.load_state_dict as used by scripts/demo.py:110
+ *                                     (key names + shapes = the reference state_dict)
+ *   migan_forward                     Generator.forward(x)          lib/model_zoo/migan_inference.py:362-369
+ *   migan_forward_host                scripts/demo.py:131-136 (x.to(device) -> model(x) -> .cpu())
+ *   b200_upfirdn2d                    _plugin.upfirdn2d(...)        torch_utils/ops/upfirdn2d.cpp:16-94
+ *   b200_bias_act                     _plugin.bias_act(...)         torch_utils/ops/bias_act.cpp:32-90 (grad == 0)
+ *
+ * Conventions: every function returns 0 on success and a non-zero code on failure, after
+ * which migan_last_error() describes the failure (thread-local string).  All device pointers
+ * are fp32, 16-byte aligned, on the device the context was created for; `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Nothing here falls back to
+ * the CPU: without a CUDA device every compute entry point fails with MIGAN_ERR_CUDA.
+ */
+#ifndef MIGAN_B200_H_
+#define MIGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIGAN_OK 0
+#define MIGAN_ERR_INVALID 1   /* bad argument (shape, resolution, null pointer, unknown key) */
+#define MIGAN_ERR_CUDA 2      /* a CUDA runtime/driver call or kernel launch failed */
+#define MIGAN_ERR_STATE 3     /* call order (e.g. forward before weights are finalized) */
+#define MIGAN_ERR_WORKSPACE 4 /* workspace too small or misaligned */
+
+/* Contraction engine for the 1x1 pointwise convs. */
+#define MIGAN_PATH_SIMT 0     /* fp32 CUDA-core FMA (bring-up / cross-check path) */
+#define MIGAN_PATH_TC 1       /* tcgen05 tensor cores, fp16 hi/lo 3-pass split, fp32 accumulate (fp32-faithful) */
+#define MIGAN_PATH_TC_FAST 2  /* tcgen05, single fp16 pass (stated lower accuracy) */
+
+typedef struct migan_ctx migan_ctx;
+
+const char* migan_last_error(void);
+const char* migan_version(void);
+
+/* Generator(resolution): resolution must be a power of two >= 8 (reference raises ValueError
+ * otherwise, migan_inference.py:214-216).  `device` is a CUDA ordinal. */
+int migan_create(int resolution, int device, migan_ctx** out);
+int migan_destroy(migan_ctx* ctx);
+
+/* Number of state_dict entries the context expects and their names/shapes, in the reference's
+ * own state_dict order (154 keys @256, 177 @512). */
+int migan_num_weights(const migan_ctx* ctx);
+int migan_weight_info(const migan_ctx* ctx, int index, const char** name, int* ndim, int64_t shape[4]);
+
+/* Copy one state_dict tensor (HOST pointer, fp32, contiguous, reference layout OIHW etc.).
+ * Unknown names or wrong element counts fail with MIGAN_ERR_INVALID. */
+int migan_set_weight(migan_ctx* ctx, const char* name, const float* host_data, int64_t numel);
+/* Validate that every key was provided (and that filter_const is the zero-insertion pattern the
+ * kernels implement), repack for the kernels (NHWC tap-major depthwise weights, K-major fp16
+ * hi/lo pointwise weights, pre-multiplied noise) and upload.  Synchronous. */
+int migan_finalize_weights(migan_ctx* ctx);
+
+/* Scratch memory the caller must provide to migan_forward for a batch of n images. */
+size_t migan_workspace_bytes(const migan_ctx* ctx, int n);
+
+/* y[n,3,R,R] = Generator.forward(x[n,4,R,R]); x, y, workspace are DEVICE pointers (NCHW fp32,
+ * contiguous).  Asynchronous on `stream`. */
+int migan_forward(migan_ctx* ctx, const float* x, float* y, int n,
+                  void* workspace, size_t workspace_bytes, int path, void* stream);
+
+/* Same with HOST x / y (pinned for full speed): H2D copy, forward, D2H copy, stream
+ * synchronize.  The device staging buffers live at the end of the workspace:
+ * workspace_bytes must be >= migan_workspace_bytes(n) + migan_host_staging_bytes(n). */
+size_t migan_host_staging_bytes(const migan_ctx* ctx, int n);
+int migan_forward_host(migan_ctx* ctx, const float* x_host, float* y_host, int n,
+                       void* workspace, size_t workspace_bytes, int path, void* stream);
+
+/* Kernels launched by the most recent migan_forward on this context. */
+int migan_last_launch_count(const migan_ctx* ctx);
+
+/* Debug/test tap: during the next forwards, copy the named intermediate (converted to NCHW
+ * fp32) into `dst` (device pointer, large enough).  name == NULL clears the tap.  Names follow
+ * the oracle's tap names (oracle/migan_oracle.py), e.g. "encoder.b256.conv1.out". */
+int migan_set_tap(migan_ctx* ctx, const char* name, float* dst);
+/* Enumerate tap names produced by a forward on `path` (index from 0; returns MIGAN_ERR_INVALID
+ * past the end).  shape = {C, H, W} of one image. */
+int migan_tap_info(const migan_ctx* ctx, int path, int index, const char** name, int shape[3]);
+
+/* upfirdn2d(x[n,c,h,w], f[fh,fw]) -> y[n,c,oh,ow], oh = (h*upy + pady0 + pady1 - fh + downy) / downy
+ * (upfirdn2d.cpp:32-33).  f == NULL means the 1x1 identity filter.  Device pointers. */
+int b200_upfirdn2d(const float* x, const float* f, float* y, int n, int c, int h, int w, int fh, int fw,
+                   int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1,
+                   int flip_filter, float gain, void* stream);
+
+/* bias_act forward: y = clamp(gain * act(x + b)), b indexed along the dimension whose stride is
+ * step_b and size size_b (bias_act.cpp:72-73: (xi / stepB) % sizeB); b == NULL: no bias.
+ * act: 1 linear 2 relu 3 lrelu 4 tanh 5 sigmoid 6 elu 7 selu 8 softplus 9 swish (bias_act.py:22-32);
+ * clamp < 0 disables clamping. */
+int b200_bias_act(const float* x, const float* b, float* y, int64_t numel, int64_t step_b, int size_b,
+                  int act, float alpha, float gain, float clamp, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIGAN_B200_H_ */

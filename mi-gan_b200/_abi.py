@@ -1,0 +1,76 @@
+"""ctypes binding of include/migan_b200.h.  Fails loudly when the library is missing:
+there is no Python/CPU fallback for the compute path."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+from . import build as _build
+
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_WORKSPACE = 0, 1, 2, 3, 4
+PATH_SIMT, PATH_TC, PATH_TC_FAST = 0, 1, 2
+PATHS = {"simt": PATH_SIMT, "tc": PATH_TC, "tc_fast": PATH_TC_FAST}
+
+# Every symbol include/migan_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("migan_last_error", c_char_p, []),
+    ("migan_version", c_char_p, []),
+    ("migan_create", c_int, [c_int, c_int, POINTER(c_void_p)]),
+    ("migan_destroy", c_int, [c_void_p]),
+    ("migan_num_weights", c_int, [c_void_p]),
+    ("migan_weight_info", c_int, [c_void_p, c_int, POINTER(c_char_p), POINTER(c_int), POINTER(c_int64)]),
+    ("migan_set_weight", c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    ("migan_finalize_weights", c_int, [c_void_p]),
+    ("migan_workspace_bytes", c_size_t, [c_void_p, c_int]),
+    ("migan_forward", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    ("migan_host_staging_bytes", c_size_t, [c_void_p, c_int]),
+    ("migan_forward_host", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    ("migan_last_launch_count", c_int, [c_void_p]),
+    ("migan_set_tap", c_int, [c_void_p, c_char_p, c_void_p]),
+    ("migan_tap_info", c_int, [c_void_p, c_int, c_int, POINTER(c_char_p), POINTER(c_int)]),
+    ("b200_upfirdn2d", c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 14 + [c_int, c_float, c_void_p]),
+    ("b200_bias_act", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_float, c_float, c_void_p]),
+]
+
+_lib = None
+
+
+class MiganError(RuntimeError):
+    """A C-ABI call returned a non-zero code."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__("migan_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+def library_path() -> str:
+    return os.environ.get("MIGAN_B200_LIB", _build.LIBPATH)
+
+
+def load(build_if_missing: bool = False):
+    """dlopen the shared library and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        if build_if_missing:
+            _build.build()
+        else:
+            raise ImportError(
+                "migan_b200: %s not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU / pure-PyTorch fallback." % path)
+    lib = ctypes.CDLL(path)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the export is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().migan_last_error()
+        raise MiganError(rc, msg.decode() if msg else "unknown error")

@@ -1,0 +1,366 @@
+// CUDA-core kernels of the MI-GAN generator forward (sm_100a): everything that is not the
+// 1x1 pointwise contraction.  All are HBM-bound streaming kernels: NHWC fp32, one 128-bit
+// vector of 4 channels per thread so that a warp touches whole 128-byte lines.
+//
+// Reference semantics (lib/model_zoo/migan_inference.py):
+//   stem      : EncoderBlock.fromrgb + activation                       :193-196
+//   dw3x3     : SeparableConv2d.conv1 (depthwise, pad 1) + activation    :155-157
+//   dw3x3_down: the same followed by Downsample2d (4x4, stride 2, pad 1) :159-160, :62-76
+//   up2       : Upsample2d (zero insertion, pad (2,1,2,1), 4x4 FIR) + noise + activation,
+//               then the decoder skip add                                :98-103, :165-169, :304-305
+//   torgb     : SynthesisBlock torgb 1x1 + Upsample2d of the image + add :308-313
+#include "common.cuh"
+#include "kernels.h"
+
+namespace migan {
+
+static inline unsigned blocks_for(int64_t items, int threads) {
+    return (unsigned)((items + threads - 1) / threads);
+}
+
+// --------------------------------------------------------------------------------------
+// stem: x NCHW [n,4,H,W] -> NHWC [n,H,W,C0]
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stem_fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                    float* __restrict__ out, int64_t npix, int HW, int C0) {
+    const int cv = C0 >> 2;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix * cv) return;
+    const int c4 = (int)(idx % cv);
+    const int64_t p = idx / cv;
+    const int64_t img = p / HW;
+    const int64_t q = p - img * HW;
+    const float* xp = x + img * 4 * (int64_t)HW + q;
+    const float x0 = __ldg(xp), x1 = __ldg(xp + HW), x2 = __ldg(xp + 2 * (int64_t)HW), x3 = __ldg(xp + 3 * (int64_t)HW);
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c4 * 4 + j;
+        const float4 wc = ldg4(w + c * 4);
+        float v = wc.x * x0;
+        v = fmaf(wc.y, x1, v);
+        v = fmaf(wc.z, x2, v);
+        v = fmaf(wc.w, x3, v);
+        o[j] = lrelu_agc(v + __ldg(b + c));
+    }
+    stg4(out + p * C0 + c4 * 4, make_float4(o[0], o[1], o[2], o[3]));
+}
+
+cudaError_t launch_stem(const float* x, const float* w, const float* b, float* out,
+                        int n, int H, int W, int C0, cudaStream_t s) {
+    const int64_t npix = (int64_t)n * H * W;
+    const int64_t items = npix * (C0 / 4);
+    stem_fromrgb_kernel<<<blocks_for(items, 256), 256, 0, s>>>(x, w, b, out, npix, H * W, C0);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// depthwise 3x3 + bias + act, NHWC -> NHWC (used by the CUDA-core path; the tcgen05 path
+// fuses this stage into the GEMM prologue)
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dw3x3_act_kernel(const float* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ bias,
+                 float* __restrict__ out, int64_t npix, int H, int W, int C) {
+    const int cv = C >> 2;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix * cv) return;
+    const int c = (int)(idx % cv) * 4;
+    const int64_t p = idx / cv;
+    const int x = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    float4 acc = ldg4(bias + c);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = x + kx - 1;
+            if (xx < 0 || xx >= W) continue;
+            const int64_t q = p + (int64_t)(ky - 1) * W + (kx - 1);
+            fma4(acc, ldg4(w9 + (ky * 3 + kx) * C + c), ldg4(in + q * C + c));
+        }
+    }
+    stg4(out + p * C + c, lrelu_agc4(acc));
+}
+
+cudaError_t launch_dw3x3(const float* in, const float* w9, const float* bias, float* out,
+                         int n, int H, int W, int C, cudaStream_t s) {
+    const int64_t npix = (int64_t)n * H * W;
+    dw3x3_act_kernel<<<blocks_for(npix * (C / 4), 256), 256, 0, s>>>(in, w9, bias, out, npix, H, W, C);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// depthwise 3x3 + bias + act + FIR 4x4 / stride 2 / pad 1, smem-tiled.
+//   block = TH x TW low-res outputs x CC channels of one image
+//   s_in : (2TH+4) x (2TW+4) input pixels (zero outside the image = conv padding 1)
+//   s_dw : (2TH+2) x (2TW+2) activated depthwise outputs (zero outside the image = FIR padding 1;
+//          NOT act(bias): the FIR pads the activated tensor, migan_inference.py:62-70)
+// --------------------------------------------------------------------------------------
+template <int TH, int TW, int CC>
+__global__ void __launch_bounds__(256)
+dw3x3_down_kernel(const float* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ bias,
+                  const float* __restrict__ fir16, float* __restrict__ out_f32,
+                  __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int C) {
+    constexpr int IH = 2 * TH + 4, IW = 2 * TW + 4, DH = 2 * TH + 2, DW = 2 * TW + 2, CV = CC / 4;
+    extern __shared__ float4 smem_f4[];
+    float4* s_in = smem_f4;
+    float4* s_dw = smem_f4 + IH * IW * CV;
+
+    const int H2 = H >> 1, W2 = W >> 1;
+    const int tiles_x = (W2 + TW - 1) / TW;
+    const int ox0 = (blockIdx.x % tiles_x) * TW;
+    const int oy0 = (blockIdx.x / tiles_x) * TH;
+    const int c0 = blockIdx.y * CC;
+    const int64_t img = blockIdx.z;
+    const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < IH * IW * CV; i += 256) {
+        const int cv = i % CV, pos = i / CV;
+        const int gy = iy0 + pos / IW, gx = ix0 + pos % IW;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+            v = ldg4(in + ((img * H + gy) * W + gx) * C + c0 + cv * 4);
+        s_in[i] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < DH * DW * CV; i += 256) {
+        const int cv = i % CV, pos = i / CV;
+        const int dy = pos / DW, dx = pos % DW;
+        const int gy = 2 * oy0 - 1 + dy, gx = 2 * ox0 - 1 + dx;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const int c = c0 + cv * 4;
+            float4 acc = ldg4(bias + c);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+                    fma4(acc, ldg4(w9 + (ky * 3 + kx) * C + c), s_in[((dy + ky) * IW + dx + kx) * CV + cv]);
+            r = lrelu_agc4(acc);
+        }
+        s_dw[i] = r;
+    }
+    __syncthreads();
+    for (int i = tid; i < TH * TW * CV; i += 256) {
+        const int cv = i % CV, pos = i / CV;
+        const int oy = pos / TW, ox = pos % TW;
+        if (oy0 + oy >= H2 || ox0 + ox >= W2) continue;
+        const int c = c0 + cv * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ty = 0; ty < 4; ++ty)
+#pragma unroll
+            for (int tx = 0; tx < 4; ++tx)
+                fma4(acc, ldg4(fir16 + (ty * 4 + tx) * C + c), s_dw[((2 * oy + ty) * DW + 2 * ox + tx) * CV + cv]);
+        const int64_t o = ((img * H2 + oy0 + oy) * W2 + ox0 + ox) * C + c;
+        if (out_f32) stg4(out_f32 + o, acc);
+        if (out_hi) {
+            __half h[4], l[4];
+            split_f16(acc.x, kActSplitScale, h[0], l[0]);
+            split_f16(acc.y, kActSplitScale, h[1], l[1]);
+            split_f16(acc.z, kActSplitScale, h[2], l[2]);
+            split_f16(acc.w, kActSplitScale, h[3], l[3]);
+            *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(h);
+            *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(l);
+        }
+    }
+}
+
+cudaError_t configure_elementwise() {
+    constexpr int TH = 8, TW = 8, CC = 32;
+    constexpr size_t smem = ((2 * TH + 4) * (2 * TW + 4) + (2 * TH + 2) * (2 * TW + 2)) * CC * sizeof(float);
+    return cudaFuncSetAttribute(dw3x3_down_kernel<TH, TW, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+cudaError_t launch_dw3x3_down(const float* in, const float* w9, const float* bias, const float* fir16,
+                              float* out_f32, __half* out_hi, __half* out_lo,
+                              int n, int H, int W, int C, cudaStream_t s) {
+    constexpr int TH = 8, TW = 8, CC = 32;
+    constexpr size_t smem = ((2 * TH + 4) * (2 * TW + 4) + (2 * TH + 2) * (2 * TW + 2)) * CC * sizeof(float);
+    auto kern = dw3x3_down_kernel<TH, TW, CC>;
+    const int H2 = H / 2, W2 = W / 2;
+    dim3 grid(((W2 + TW - 1) / TW) * ((H2 + TH - 1) / TH), C / CC, n);
+    kern<<<grid, 256, smem, s>>>(in, w9, bias, fir16, out_f32, out_hi, out_lo, H, W, C);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// 2x FIR up-sampling (polyphase: only the taps that meet a non-zero of the zero-inserted
+// signal) + noise + act + skip.  out[o] = sum_t f[t] * z[o + t - 2], z[2i] = x[i], z[odd] = 0.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+up2_noise_act_skip_kernel(const float* __restrict__ t, const float* __restrict__ fir16,
+                          const float* __restrict__ noise, const float* __restrict__ skip,
+                          float* __restrict__ out, int64_t npix_out, int h, int w, int C) {
+    const int cv = C >> 2;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix_out * cv) return;
+    const int c = (int)(idx % cv) * 4;
+    const int64_t p = idx / cv;
+    const int W2 = 2 * w, H2 = 2 * h;
+    const int ox = (int)(p % W2);
+    const int oy = (int)((p / W2) % H2);
+    const int64_t img = p / ((int64_t)W2 * H2);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int ty = (oy & 1) + 2 * a;
+        const int iy = (oy + ty - 2) >> 1;
+        if (iy < 0 || iy >= h) continue;
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
+            const int tx = (ox & 1) + 2 * bb;
+            const int ix = (ox + tx - 2) >> 1;
+            if (ix < 0 || ix >= w) continue;
+            fma4(acc, ldg4(fir16 + (ty * 4 + tx) * C + c), ldg4(t + ((img * h + iy) * w + ix) * C + c));
+        }
+    }
+    if (noise) {
+        const float nz = __ldg(noise + oy * W2 + ox);
+        acc.x += nz; acc.y += nz; acc.z += nz; acc.w += nz;
+    }
+    acc = lrelu_agc4(acc);
+    if (skip) {
+        const float4 sk = ldg4(skip + p * C + c);
+        acc.x += sk.x; acc.y += sk.y; acc.z += sk.z; acc.w += sk.w;
+    }
+    stg4(out + p * C + c, acc);
+}
+
+cudaError_t launch_up2(const float* t, const float* fir16, const float* noise, const float* skip,
+                       float* out, int n, int h, int w, int C, cudaStream_t s) {
+    const int64_t npix = (int64_t)n * 4 * h * w;
+    up2_noise_act_skip_kernel<<<blocks_for(npix * (C / 4), 256), 256, 0, s>>>(t, fir16, noise, skip, out, npix, h, w, C);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// torgb (C -> 3, with bias) + up-sampled previous image.  G lanes cooperate on one pixel
+// (128-bit loads along C, warp-shuffle reduction), lane 0 of the group writes 3 planes.
+// --------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256)
+torgb_img_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                 const float* __restrict__ img_lo, const float* __restrict__ fir, float* __restrict__ img_out,
+                 int64_t npix, int r, int C) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % G;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t p = warp_global * (32 / G) + lane / G;
+    const bool valid = p < npix;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (valid) {
+        for (int c4 = sub; c4 < (C >> 2); c4 += G) {
+            const float4 v = ldg4(x + p * C + c4 * 4);
+            const float4 w0 = ldg4(w + c4 * 4), w1 = ldg4(w + C + c4 * 4), w2 = ldg4(w + 2 * C + c4 * 4);
+            a0 = fmaf(v.x, w0.x, a0); a0 = fmaf(v.y, w0.y, a0); a0 = fmaf(v.z, w0.z, a0); a0 = fmaf(v.w, w0.w, a0);
+            a1 = fmaf(v.x, w1.x, a1); a1 = fmaf(v.y, w1.y, a1); a1 = fmaf(v.z, w1.z, a1); a1 = fmaf(v.w, w1.w, a1);
+            a2 = fmaf(v.x, w2.x, a2); a2 = fmaf(v.y, w2.y, a2); a2 = fmaf(v.z, w2.z, a2); a2 = fmaf(v.w, w2.w, a2);
+        }
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+    }
+    if (!valid || sub != 0) return;
+    const int ox = (int)(p % r);
+    const int oy = (int)((p / r) % r);
+    const int64_t img = p / ((int64_t)r * r);
+    float acc[3] = {a0 + __ldg(b), a1 + __ldg(b + 1), a2 + __ldg(b + 2)};
+    if (img_lo) {
+        const int h = r >> 1;
+        float up[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int ty = (oy & 1) + 2 * a;
+            const int iy = (oy + ty - 2) >> 1;
+            if (iy < 0 || iy >= h) continue;
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+                const int tx = (ox & 1) + 2 * bb;
+                const int ix = (ox + tx - 2) >> 1;
+                if (ix < 0 || ix >= h) continue;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    up[k] = fmaf(__ldg(fir + (ty * 4 + tx) * 3 + k),
+                                 __ldg(img_lo + ((img * 3 + k) * h + iy) * h + ix), up[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[k] = up[k] + acc[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) img_out[((img * 3 + k) * r + oy) * r + ox] = acc[k];
+}
+
+cudaError_t launch_torgb(const float* x, const float* w, const float* b, const float* img_lo,
+                         const float* fir16x3, float* img_out, int n, int r, int C, cudaStream_t s) {
+    const int64_t npix = (int64_t)n * r * r;
+    if (C / 4 >= 32) {
+        const int64_t threads = npix * 32;
+        torgb_img_kernel<32><<<blocks_for(threads, 256), 256, 0, s>>>(x, w, b, img_lo, fir16x3, img_out, npix, r, C);
+    } else {
+        const int64_t threads = npix * 16;
+        torgb_img_kernel<16><<<blocks_for(threads, 256), 256, 0, s>>>(x, w, b, img_lo, fir16x3, img_out, npix, r, C);
+    }
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+add_inplace_kernel(float* __restrict__ x, const float* __restrict__ y, int64_t n4) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 a = reinterpret_cast<float4*>(x)[i];
+    const float4 b = __ldg(reinterpret_cast<const float4*>(y) + i);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(x)[i] = a;
+}
+
+cudaError_t launch_add(float* x, const float* y, int64_t numel, cudaStream_t s) {
+    add_inplace_kernel<<<blocks_for(numel / 4, 256), 256, 0, s>>>(x, y, numel / 4);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total, int HW, int C) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index into NCHW output
+    if (i >= total) return;
+    const int64_t q = i % HW;
+    const int64_t c = (i / HW) % C;
+    const int64_t img = i / ((int64_t)HW * C);
+    out[i] = __ldg(in + (img * HW + q) * C + c);
+}
+
+cudaError_t launch_nhwc_to_nchw(const float* in, float* out, int n, int H, int W, int C, cudaStream_t s) {
+    const int64_t total = (int64_t)n * H * W * C;
+    nhwc_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, s>>>(in, out, total, H * W, C);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, float scale, int64_t n4) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    __half h[4], l[4];
+    split_f16(v.x, scale, h[0], l[0]);
+    split_f16(v.y, scale, h[1], l[1]);
+    split_f16(v.z, scale, h[2], l[2]);
+    split_f16(v.w, scale, h[3], l[3]);
+    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+    reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+}
+
+cudaError_t launch_split_f16(const float* in, __half* hi, __half* lo, float scale, int64_t numel, cudaStream_t s) {
+    split_f16_kernel<<<blocks_for(numel / 4, 256), 256, 0, s>>>(in, hi, lo, scale, numel / 4);
+    return cudaGetLastError();
+}
+
+}  // namespace migan

@@ -1,0 +1,54 @@
+// Internal launcher interface between the plan executor (migan_abi.cu) and the kernels.
+// Activations are NHWC fp32 in HBM ([n, H, W, C], C a multiple of 4, 16-byte aligned);
+// the RGB image path is planar NCHW fp32 ([n, 3, r, r]) so the last level is the output.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace migan {
+
+// Per-device one-time setup (dynamic shared memory opt-in); called by migan_create.
+cudaError_t configure_elementwise();
+cudaError_t configure_sepconv_tc();
+
+// ---- CUDA-core kernels (elementwise.cu) ---------------------------------------------
+// fromrgb 1x1 (4 -> C0) + bias + lrelu_agc;  x NCHW [n,4,H,W] -> out NHWC [n,H,W,C0]
+cudaError_t launch_stem(const float* x_nchw, const float* w, const float* b, float* out,
+                        int n, int H, int W, int C0, cudaStream_t s);
+// depthwise 3x3 (pad 1) + bias + lrelu_agc, NHWC -> NHWC.  w9 is tap-major [9][C].
+cudaError_t launch_dw3x3(const float* in, const float* w9, const float* bias, float* out,
+                         int n, int H, int W, int C, cudaStream_t s);
+// depthwise 3x3 + bias + lrelu_agc, then 4x4 FIR stride 2 pad 1 (taps fir16 [16][C]).
+// Writes fp32 [n,H/2,W/2,C] to out_f32 (if non-null) and/or the scaled fp16 hi/lo split
+// (if out_hi non-null) that the tcgen05 GEMM consumes directly through TMA.
+cudaError_t launch_dw3x3_down(const float* in, const float* w9, const float* bias, const float* fir16,
+                              float* out_f32, __half* out_hi, __half* out_lo,
+                              int n, int H, int W, int C, cudaStream_t s);
+// 2x polyphase FIR up-sampling of the raw 1x1-conv output + noise + lrelu_agc + skip add.
+// t [n,h,w,C] -> out [n,2h,2w,C]; fir16 [16][C] (gain included); noise [2h*2w] (already
+// multiplied by noise_strength) or null; skip [n,2h,2w,C] or null (added AFTER the activation).
+cudaError_t launch_up2(const float* t, const float* fir16, const float* noise, const float* skip,
+                       float* out, int n, int h, int w, int C, cudaStream_t s);
+// img_out[n,3,r,r] = up2(img_lo[n,3,r/2,r/2]) + torgb(x[n,r,r,C]) + b;  img_lo may be null (b4).
+cudaError_t launch_torgb(const float* x, const float* w, const float* b, const float* img_lo,
+                         const float* fir16x3, float* img_out, int n, int r, int C, cudaStream_t s);
+cudaError_t launch_add(float* x, const float* y, int64_t numel, cudaStream_t s);
+cudaError_t launch_nhwc_to_nchw(const float* in, float* out, int n, int H, int W, int C, cudaStream_t s);
+cudaError_t launch_split_f16(const float* in, __half* hi, __half* lo, float scale, int64_t numel, cudaStream_t s);
+
+// ---- fp32 CUDA-core GEMM for the 1x1 conv (gemm_simt.cu) ----------------------------
+// out[p][n] = epilogue( sum_k A[p][k] * Bt[k][n] ), A [P][K], Bt [K][N], out [P][N].
+// epilogue: + noise[p % HW] (if noise) then lrelu_agc (if act).
+cudaError_t launch_pw_gemm_simt(const float* A, const float* Bt, float* out, int64_t P, int K, int N,
+                                const float* noise, int HW, int act, cudaStream_t s);
+
+// ---- standalone ops (ops.cu) ---------------------------------------------------------
+cudaError_t launch_upfirdn2d(const float* x, const float* f, float* y, int n, int c, int h, int w,
+                             int fh, int fw, int upx, int upy, int downx, int downy,
+                             int padx0, int padx1, int pady0, int pady1, int flip, float gain,
+                             int oh, int ow, cudaStream_t s);
+cudaError_t launch_bias_act(const float* x, const float* b, float* y, int64_t numel, int64_t step_b, int size_b,
+                            int act, float alpha, float gain, float clamp, cudaStream_t s);
+
+}  // namespace migan

@@ -1,0 +1,799 @@
+// C ABI + host runtime of the B200-native MI-GAN generator (include/migan_b200.h).
+//
+// Host side of the hot path: weight registry in the reference's state_dict layout, one-time
+// repacking for the kernels, a per-batch-size execution plan (a flat list of kernel launches
+// with every pointer / tensor map resolved) and the launcher.  Replaces the module tree of
+// lib/model_zoo/migan_inference.py:173-369 (EncoderBlock / Encoder / SynthesisBlock* /
+// Synthesis / Generator): the control flow of those forward() methods is the plan below.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/migan_b200.h"
+#include "kernels.h"
+#include "sepconv_tc.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(MIGAN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+inline int channels(int res) { return std::min(32768 / res, 512); }  // migan_inference.py:222-223
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WeightSpec {
+    std::string name;
+    int ndim;
+    int64_t shape[4];
+    int64_t numel() const {
+        int64_t n = 1;
+        for (int i = 0; i < ndim; ++i) n *= shape[i];
+        return n;
+    }
+};
+
+// One SeparableConv2d (migan_inference.py:106-170), packed for the kernels.
+struct SepConv {
+    std::string p;  // state_dict prefix, e.g. "encoder.b256.conv2."
+    int cin = 0, cout = 0;
+    int res_in = 0;   // spatial size the depthwise conv runs at
+    int res_pw = 0;   // spatial size the 1x1 conv runs at (res_in / 2 if down)
+    int res_out = 0;  // output spatial size (2 * res_pw if up)
+    bool down = false, up = false, noise = false;
+    // device pointers into the weight arena
+    float* w9 = nullptr;      // [9][cin]   depthwise taps, tap-major
+    float* bias = nullptr;    // [cin]
+    float* pw_t = nullptr;    // [cin][cout] fp32 (CUDA-core GEMM)
+    __half* pw_hi = nullptr;  // [cout][cin] fp16 hi part of w * 2^k   (tcgen05, K-major)
+    __half* pw_lo = nullptr;  // [cout][cin] fp16 lo part
+    float tc_inv_scale = 1.f; // 1 / (kActSplitScale * 2^k)
+    float* fir16 = nullptr;   // [16][cin] (down) or [16][cout] (up), tap-major
+    float* noise_dev = nullptr;  // [res_out^2] = noise_const * noise_strength
+};
+
+struct ToRgb {
+    std::string p;  // "synthesis.b64."
+    int c = 0, res = 0;
+    bool has_up = false;
+    float* w = nullptr;    // [3][c]
+    float* b = nullptr;    // [3]
+    float* fir = nullptr;  // [16][3]
+};
+
+enum StepKind { K_STEM, K_DW, K_DWDOWN, K_GEMM_SIMT, K_SEPCONV_TC, K_UP2, K_TORGB, K_ADD };
+
+constexpr int PTR_X = 1, PTR_Y = 2;  // flags: operand is the caller's x / y
+
+struct Step {
+    StepKind kind;
+    const SepConv* L = nullptr;
+    const ToRgb* T = nullptr;
+    const float* in = nullptr;
+    const float* aux = nullptr;  // skip tensor / low-res image / noise
+    float* out = nullptr;
+    __half* hi = nullptr;
+    __half* lo = nullptr;
+    int io_flags = 0;
+    int n = 0, H = 0, W = 0, C = 0;  // meaning depends on kind (input dims)
+    int act = 0;
+    bool want_f32 = false;
+    migan::SepconvTcArgs tc;  // resolved tcgen05 launch (tensor maps, tiling)
+    // tap (debug): tensor produced by this step
+    std::string tap;
+    const float* tap_src = nullptr;
+    int tapC = 0, tapH = 0, tapW = 0;
+    bool tap_planar = false;
+    int tap_flags = 0;
+};
+
+struct Plan {
+    int n = 0, path = -1;
+    void* ws = nullptr;
+    std::vector<Step> steps;
+};
+
+}  // namespace
+
+struct migan_ctx {
+    int resolution = 0, device = 0;
+    std::vector<WeightSpec> specs;
+    std::map<std::string, int> spec_index;
+    std::vector<std::vector<float>> host;  // host copies, by spec index
+    std::vector<bool> provided;
+    bool finalized = false;
+
+    std::vector<int> enc_res;  // R .. 4
+    std::vector<int> syn_res;  // 4 .. R
+    // encoder
+    float* fromrgb_w = nullptr;  // [C0][4]
+    float* fromrgb_b = nullptr;
+    std::vector<SepConv> enc1, enc2;  // per enc_res entry
+    // synthesis
+    std::vector<SepConv> syn1, syn2;  // per syn_res entry
+    std::vector<ToRgb> torgb;
+    void* arena = nullptr;
+
+    Plan plan;
+    int last_launches = 0;
+    std::string tap_name;
+    float* tap_dst = nullptr;
+};
+
+namespace {
+
+void add_spec(migan_ctx* c, const std::string& name, std::initializer_list<int64_t> shape) {
+    WeightSpec s;
+    s.name = name;
+    s.ndim = (int)shape.size();
+    int i = 0;
+    for (int64_t d : shape) s.shape[i++] = d;
+    for (; i < 4; ++i) s.shape[i] = 1;
+    c->spec_index[name] = (int)c->specs.size();
+    c->specs.push_back(s);
+}
+
+// Key order = the reference state_dict (own params, own buffers, then children).
+void add_sepconv_specs(migan_ctx* c, const SepConv& L) {
+    if (L.noise) {
+        add_spec(c, L.p + "noise_strength", {});
+        add_spec(c, L.p + "noise_const", {L.res_out, L.res_out});
+    }
+    add_spec(c, L.p + "conv1.weight", {L.cin, 1, 3, 3});
+    add_spec(c, L.p + "conv1.bias", {L.cin});
+    add_spec(c, L.p + "conv2.weight", {L.cout, L.cin, 1, 1});
+    if (L.down) add_spec(c, L.p + "downsample.filter.weight", {L.cin, 1, 4, 4});
+    if (L.up) {
+        add_spec(c, L.p + "upsample.filter_const", {1, 1, L.res_out, L.res_out});
+        add_spec(c, L.p + "upsample.filter.weight", {L.cout, 1, 4, 4});
+    }
+}
+
+SepConv make_sepconv(const std::string& p, int cin, int cout, int res_in, bool down, bool up, bool noise) {
+    SepConv L;
+    L.p = p; L.cin = cin; L.cout = cout; L.res_in = res_in;
+    L.down = down; L.up = up; L.noise = noise;
+    L.res_pw = down ? res_in / 2 : res_in;
+    L.res_out = up ? L.res_pw * 2 : L.res_pw;
+    return L;
+}
+
+const std::vector<float>& W(const migan_ctx* c, const std::string& name) {
+    return c->host[c->spec_index.at(name)];
+}
+
+// Bump allocator over a host staging image of the device weight arena.
+struct ArenaBuilder {
+    std::vector<unsigned char> bytes;
+    size_t alloc(size_t n) {
+        size_t off = align_up(bytes.size(), 256);
+        bytes.resize(off + n, 0);
+        return off;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* migan_last_error(void) { return g_last_error.c_str(); }
+const char* migan_version(void) { return "migan_b200 0.1 (sm_100a)"; }
+
+int migan_create(int resolution, int device, migan_ctx** out) {
+    if (!out) return fail(MIGAN_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int log2res = 0;
+    while ((1 << (log2res + 1)) <= resolution) ++log2res;
+    if (resolution < 8 || (1 << log2res) != resolution || resolution > 4096)
+        return fail(MIGAN_ERR_INVALID, "resolution must be a power of two in [8, 4096], got %d", resolution);
+    std::unique_ptr<migan_ctx> c(new migan_ctx);
+    c->resolution = resolution;
+    c->device = device;
+    for (int i = log2res; i >= 2; --i) c->enc_res.push_back(1 << i);
+    for (int i = 2; i <= log2res; ++i) c->syn_res.push_back(1 << i);
+
+    // synthesis first, then encoder (ctor order migan_inference.py:359-360)
+    const int c4 = channels(4);
+    c->syn1.push_back(make_sepconv("synthesis.b4.conv1.", c4, c4, 4, false, false, false));
+    c->syn2.push_back(make_sepconv("synthesis.b4.conv2.", c4, c4, 4, false, false, false));
+    for (size_t i = 1; i < c->syn_res.size(); ++i) {
+        const int rj = c->syn_res[i], ri = c->syn_res[i - 1];
+        const std::string p = "synthesis.b" + std::to_string(rj) + ".";
+        c->syn1.push_back(make_sepconv(p + "conv1.", channels(ri), channels(rj), ri, false, true, true));
+        c->syn2.push_back(make_sepconv(p + "conv2.", channels(rj), channels(rj), rj, false, false, true));
+    }
+    for (size_t i = 0; i < c->syn_res.size(); ++i) {
+        const int r = c->syn_res[i];
+        const std::string p = "synthesis.b" + std::to_string(r) + ".";
+        add_sepconv_specs(c.get(), c->syn1[i]);
+        add_sepconv_specs(c.get(), c->syn2[i]);
+        add_spec(c.get(), p + "torgb.weight", {3, channels(r), 1, 1});
+        add_spec(c.get(), p + "torgb.bias", {3});
+        ToRgb t;
+        t.p = p; t.c = channels(r); t.res = r; t.has_up = (i > 0);
+        if (t.has_up) {
+            add_spec(c.get(), p + "upsample.filter_const", {1, 1, r, r});
+            add_spec(c.get(), p + "upsample.filter.weight", {3, 1, 4, 4});
+        }
+        c->torgb.push_back(t);
+    }
+    for (size_t i = 0; i < c->enc_res.size(); ++i) {
+        const int r = c->enc_res[i];
+        const std::string p = "encoder.b" + std::to_string(r) + ".";
+        const bool last = (i + 1 == c->enc_res.size());
+        const int ci = channels(r), cj = last ? ci : channels(c->enc_res[i + 1]);
+        if (i == 0) {
+            add_spec(c.get(), p + "fromrgb.weight", {ci, 4, 1, 1});
+            add_spec(c.get(), p + "fromrgb.bias", {ci});
+        }
+        c->enc1.push_back(make_sepconv(p + "conv1.", ci, ci, r, false, false, false));
+        c->enc2.push_back(make_sepconv(p + "conv2.", ci, cj, r, !last, false, false));
+        add_sepconv_specs(c.get(), c->enc1.back());
+        add_sepconv_specs(c.get(), c->enc2.back());
+    }
+    c->host.resize(c->specs.size());
+    c->provided.assign(c->specs.size(), false);
+
+    if (device >= 0) {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || device >= ndev) {
+            (void)cudaGetLastError();
+            return fail(MIGAN_ERR_CUDA, "CUDA device %d not available (%s; %d devices): this library has no CPU path",
+                        device, cudaGetErrorString(e), ndev);
+        }
+        CUDA_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            return fail(MIGAN_ERR_CUDA, "device %d is sm_%d%d; this build targets sm_100a (B200) only", device, prop.major, prop.minor);
+        CUDA_TRY(migan::configure_elementwise());
+        CUDA_TRY(migan::configure_sepconv_tc());
+    }  // device < 0: description-only context (weight registry / workspace sizes), cannot compute
+    *out = c.release();
+    return MIGAN_OK;
+}
+
+int migan_destroy(migan_ctx* ctx) {
+    if (!ctx) return MIGAN_OK;
+    if (ctx->arena && ctx->device >= 0) {
+        cudaSetDevice(ctx->device);
+        cudaFree(ctx->arena);
+    }
+    delete ctx;
+    return MIGAN_OK;
+}
+
+int migan_num_weights(const migan_ctx* ctx) { return ctx ? (int)ctx->specs.size() : 0; }
+
+int migan_weight_info(const migan_ctx* ctx, int index, const char** name, int* ndim, int64_t shape[4]) {
+    if (!ctx || index < 0 || index >= (int)ctx->specs.size()) return fail(MIGAN_ERR_INVALID, "bad weight index %d", index);
+    const WeightSpec& s = ctx->specs[index];
+    if (name) *name = s.name.c_str();
+    if (ndim) *ndim = s.ndim;
+    if (shape)
+        for (int i = 0; i < 4; ++i) shape[i] = s.shape[i];
+    return MIGAN_OK;
+}
+
+int migan_set_weight(migan_ctx* ctx, const char* name, const float* host_data, int64_t numel) {
+    if (!ctx || !name || !host_data) return fail(MIGAN_ERR_INVALID, "null argument");
+    auto it = ctx->spec_index.find(name);
+    if (it == ctx->spec_index.end()) return fail(MIGAN_ERR_INVALID, "unexpected key '%s' for resolution %d", name, ctx->resolution);
+    const WeightSpec& s = ctx->specs[it->second];
+    if (s.numel() != numel)
+        return fail(MIGAN_ERR_INVALID, "size mismatch for '%s': expected %lld elements, got %lld", name, (long long)s.numel(), (long long)numel);
+    ctx->host[it->second].assign(host_data, host_data + numel);
+    ctx->provided[it->second] = true;
+    ctx->finalized = false;
+    return MIGAN_OK;
+}
+
+static int pack_sepconv(migan_ctx* ctx, SepConv& L, ArenaBuilder& ab, std::vector<std::pair<void**, size_t>>& fix) {
+    const int cin = L.cin, cout = L.cout;
+    {   // depthwise taps [cin,1,3,3] -> [9][cin]
+        const std::vector<float>& w = W(ctx, L.p + "conv1.weight");
+        size_t off = ab.alloc(sizeof(float) * 9 * cin);
+        float* d = reinterpret_cast<float*>(ab.bytes.data() + off);
+        for (int c = 0; c < cin; ++c)
+            for (int t = 0; t < 9; ++t) d[t * cin + c] = w[c * 9 + t];
+        fix.push_back({reinterpret_cast<void**>(&L.w9), off});
+    }
+    {
+        const std::vector<float>& b = W(ctx, L.p + "conv1.bias");
+        size_t off = ab.alloc(sizeof(float) * cin);
+        memcpy(ab.bytes.data() + off, b.data(), sizeof(float) * cin);
+        fix.push_back({reinterpret_cast<void**>(&L.bias), off});
+    }
+    {   // pointwise [cout,cin,1,1] -> fp32 [cin][cout] and fp16 hi/lo [cout][cin]
+        const std::vector<float>& w = W(ctx, L.p + "conv2.weight");
+        size_t off = ab.alloc(sizeof(float) * cin * cout);
+        float* d = reinterpret_cast<float*>(ab.bytes.data() + off);
+        float maxabs = 0.f;
+        for (int o = 0; o < cout; ++o)
+            for (int k = 0; k < cin; ++k) {
+                d[(size_t)k * cout + o] = w[(size_t)o * cin + k];
+                if (std::isfinite(w[(size_t)o * cin + k])) maxabs = std::max(maxabs, std::fabs(w[(size_t)o * cin + k]));
+            }
+        fix.push_back({reinterpret_cast<void**>(&L.pw_t), off});
+        // power-of-two scale so the largest weight lands in [8192, 16384): hi and lo both stay
+        // well inside fp16's normal range, and the scale is undone exactly in the epilogue.
+        int k2 = 0;
+        if (maxabs > 0.f) k2 = (int)std::floor(std::log2(16384.0 / (double)maxabs));
+        k2 = std::max(-14, std::min(24, k2));
+        const float wscale = std::ldexp(1.0f, k2);
+        L.tc_inv_scale = 1.0f / (wscale * 64.0f /* kActSplitScale */);
+        size_t off_hi = ab.alloc(sizeof(__half) * cin * cout);
+        size_t off_lo = ab.alloc(sizeof(__half) * cin * cout);
+        __half* hi = reinterpret_cast<__half*>(ab.bytes.data() + off_hi);
+        __half* lo = reinterpret_cast<__half*>(ab.bytes.data() + off_lo);
+        for (size_t i = 0; i < (size_t)cin * cout; ++i) {
+            const float s = w[i] * wscale;
+            const __half h = __float2half_rn(s);
+            hi[i] = h;
+            lo[i] = __float2half_rn(s - __half2float(h));
+        }
+        fix.push_back({reinterpret_cast<void**>(&L.pw_hi), off_hi});
+        fix.push_back({reinterpret_cast<void**>(&L.pw_lo), off_lo});
+    }
+    if (L.down || L.up) {
+        const int cf = L.down ? cin : cout;
+        const std::vector<float>& f = W(ctx, L.p + (L.down ? "downsample.filter.weight" : "upsample.filter.weight"));
+        size_t off = ab.alloc(sizeof(float) * 16 * cf);
+        float* d = reinterpret_cast<float*>(ab.bytes.data() + off);
+        for (int c = 0; c < cf; ++c)
+            for (int t = 0; t < 16; ++t) d[t * cf + c] = f[c * 16 + t];
+        fix.push_back({reinterpret_cast<void**>(&L.fir16), off});
+    }
+    if (L.up) {
+        // The kernels implement zero insertion; check filter_const is that pattern (migan_inference.py:83-85).
+        const std::vector<float>& fc = W(ctx, L.p + "upsample.filter_const");
+        const int r = L.res_out;
+        for (int y = 0; y < r; ++y)
+            for (int x = 0; x < r; ++x) {
+                const float want = ((y | x) & 1) ? 0.f : 1.f;
+                if (fc[(size_t)y * r + x] != want)
+                    return fail(MIGAN_ERR_INVALID, "%supsample.filter_const is not the zero-insertion pattern at (%d,%d)", L.p.c_str(), y, x);
+            }
+    }
+    if (L.noise) {
+        const std::vector<float>& nc = W(ctx, L.p + "noise_const");
+        const float ns = W(ctx, L.p + "noise_strength")[0];
+        size_t off = ab.alloc(sizeof(float) * nc.size());
+        float* d = reinterpret_cast<float*>(ab.bytes.data() + off);
+        for (size_t i = 0; i < nc.size(); ++i) d[i] = nc[i] * ns;  // migan_inference.py:166
+        fix.push_back({reinterpret_cast<void**>(&L.noise_dev), off});
+    }
+    return MIGAN_OK;
+}
+
+int migan_finalize_weights(migan_ctx* ctx) {
+    if (!ctx) return fail(MIGAN_ERR_INVALID, "null ctx");
+    if (ctx->device < 0) return fail(MIGAN_ERR_CUDA, "context was created without a CUDA device: this library has no CPU path");
+    for (size_t i = 0; i < ctx->specs.size(); ++i)
+        if (!ctx->provided[i]) return fail(MIGAN_ERR_STATE, "missing key '%s'", ctx->specs[i].name.c_str());
+    ArenaBuilder ab;
+    std::vector<std::pair<void**, size_t>> fix;
+    {
+        const std::string p = "encoder.b" + std::to_string(ctx->resolution) + ".fromrgb.";
+        const std::vector<float>& w = W(ctx, p + "weight");
+        const std::vector<float>& b = W(ctx, p + "bias");
+        size_t ow = ab.alloc(sizeof(float) * w.size());
+        memcpy(ab.bytes.data() + ow, w.data(), sizeof(float) * w.size());
+        size_t ob = ab.alloc(sizeof(float) * b.size());
+        memcpy(ab.bytes.data() + ob, b.data(), sizeof(float) * b.size());
+        fix.push_back({reinterpret_cast<void**>(&ctx->fromrgb_w), ow});
+        fix.push_back({reinterpret_cast<void**>(&ctx->fromrgb_b), ob});
+    }
+    for (auto* vec : {&ctx->enc1, &ctx->enc2, &ctx->syn1, &ctx->syn2})
+        for (SepConv& L : *vec) {
+            int rc = pack_sepconv(ctx, L, ab, fix);
+            if (rc) return rc;
+        }
+    for (ToRgb& t : ctx->torgb) {
+        const std::vector<float>& w = W(ctx, t.p + "torgb.weight");
+        const std::vector<float>& b = W(ctx, t.p + "torgb.bias");
+        size_t ow = ab.alloc(sizeof(float) * w.size());
+        memcpy(ab.bytes.data() + ow, w.data(), sizeof(float) * w.size());
+        size_t ob = ab.alloc(sizeof(float) * 4);
+        memcpy(ab.bytes.data() + ob, b.data(), sizeof(float) * 3);
+        fix.push_back({reinterpret_cast<void**>(&t.w), ow});
+        fix.push_back({reinterpret_cast<void**>(&t.b), ob});
+        if (t.has_up) {
+            const std::vector<float>& fc = W(ctx, t.p + "upsample.filter_const");
+            for (int y = 0; y < t.res; ++y)
+                for (int x = 0; x < t.res; ++x)
+                    if (fc[(size_t)y * t.res + x] != (((y | x) & 1) ? 0.f : 1.f))
+                        return fail(MIGAN_ERR_INVALID, "%supsample.filter_const is not the zero-insertion pattern", t.p.c_str());
+            const std::vector<float>& f = W(ctx, t.p + "upsample.filter.weight");
+            size_t of = ab.alloc(sizeof(float) * 48);
+            float* d = reinterpret_cast<float*>(ab.bytes.data() + of);
+            for (int c = 0; c < 3; ++c)
+                for (int k = 0; k < 16; ++k) d[k * 3 + c] = f[c * 16 + k];
+            fix.push_back({reinterpret_cast<void**>(&t.fir), of});
+        }
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->arena) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaFree(ctx->arena));
+        ctx->arena = nullptr;
+    }
+    CUDA_TRY(cudaMalloc(&ctx->arena, ab.bytes.size()));
+    CUDA_TRY(cudaMemcpy(ctx->arena, ab.bytes.data(), ab.bytes.size(), cudaMemcpyHostToDevice));
+    for (auto& f : fix) *f.first = static_cast<unsigned char*>(ctx->arena) + f.second;
+    ctx->plan = Plan();  // pointers changed
+    ctx->finalized = true;
+    return MIGAN_OK;
+}
+
+// ---- workspace layout -------------------------------------------------------------------
+//   feats[r]  n * r^2 * ch(r) fp32, one per encoder resolution (the decoder skip inputs)
+//   S0..S2    three rotating scratch tensors of n * R^2 * ch(R) fp32 (largest activation)
+//   IMG0/1    ping-pong planar RGB images n * 3 * R^2 fp32
+static size_t feat_bytes(int n, int r) { return align_up((size_t)n * r * r * channels(r) * sizeof(float), 1024); }
+static size_t scratch_bytes(const migan_ctx* c, int n) {
+    return align_up((size_t)n * c->resolution * c->resolution * channels(c->resolution) * sizeof(float), 1024);
+}
+static size_t img_bytes(const migan_ctx* c, int n) {
+    return align_up((size_t)n * 3 * c->resolution * c->resolution * sizeof(float), 1024);
+}
+
+size_t migan_workspace_bytes(const migan_ctx* ctx, int n) {
+    if (!ctx || n <= 0) return 0;
+    size_t total = 0;
+    for (int r : ctx->enc_res) total += feat_bytes(n, r);
+    total += 3 * scratch_bytes(ctx, n) + 2 * img_bytes(ctx, n);
+    return total;
+}
+
+size_t migan_host_staging_bytes(const migan_ctx* ctx, int n) {
+    if (!ctx || n <= 0) return 0;
+    const size_t px = (size_t)n * ctx->resolution * ctx->resolution * sizeof(float);
+    return align_up(4 * px, 1024) + align_up(3 * px, 1024);
+}
+
+}  // extern "C"
+
+namespace {
+
+struct PlanBuilder {
+    migan_ctx* c;
+    int n, path;
+    unsigned char* base;
+    std::map<int, float*> feat;
+    float* S[3];
+    float* IMG[2];
+    std::vector<Step> steps;
+
+    int other(int a, int b = -1) const {
+        for (int i = 0; i < 3; ++i)
+            if (i != a && i != b) return i;
+        return 0;
+    }
+    void set_tap(Step& s, const std::string& name, const float* src, int C, int H, int W, bool planar = false, int flags = 0) {
+        s.tap = name; s.tap_src = src; s.tapC = C; s.tapH = H; s.tapW = W; s.tap_planar = planar; s.tap_flags = flags;
+    }
+
+    // Emit one SeparableConv2d reading `in` (NHWC [n,res_in,res_in,cin]); `skip` is added after the
+    // final activation (decoder conv1, migan_inference.py:304-305).  Returns the output pointer.
+    // in_idx: scratch index holding `in` (or -1 if it is a feat buffer); out_fixed: write there if non-null.
+    int emit_sepconv(const SepConv& L, const float* in, int in_idx, float* out_fixed, const float* skip, int& out_idx, float*& out_ptr) {
+        const int t1 = other(in_idx), t2 = other(in_idx, t1);
+        const bool tc = (path != MIGAN_PATH_SIMT);
+        const float* gemm_in = nullptr;
+        __half *ghi = nullptr, *glo = nullptr;
+        if (L.down) {
+            Step s; s.kind = K_DWDOWN; s.L = &L; s.in = in; s.n = n; s.H = L.res_in; s.W = L.res_in; s.C = L.cin;
+            if (tc) {
+                s.hi = reinterpret_cast<__half*>(S[t1]);
+                s.lo = s.hi + (size_t)n * L.res_pw * L.res_pw * L.cin;
+                ghi = s.hi; glo = s.lo;
+            } else {
+                s.out = S[t1]; gemm_in = S[t1];
+                set_tap(s, L.p + "down", S[t1], L.cin, L.res_pw, L.res_pw);
+            }
+            steps.push_back(s);
+        } else if (!tc) {
+            Step s; s.kind = K_DW; s.L = &L; s.in = in; s.out = S[t1]; s.n = n; s.H = L.res_in; s.W = L.res_in; s.C = L.cin;
+            set_tap(s, L.p + "dw_act", S[t1], L.cin, L.res_in, L.res_in);
+            steps.push_back(s);
+            gemm_in = S[t1];
+        }
+        // 1x1 conv at res_pw
+        float* pw_out;
+        int pw_idx;
+        const bool raw = L.up;  // up layers: noise/act happen after the FIR (K_UP2)
+        if (raw) { pw_out = S[t2]; pw_idx = t2; }
+        else if (out_fixed) { pw_out = out_fixed; pw_idx = -1; }
+        else { pw_out = S[t2]; pw_idx = t2; }
+        {
+            Step s; s.L = &L; s.n = n; s.H = L.res_pw; s.W = L.res_pw; s.C = L.cin; s.out = pw_out;
+            s.act = raw ? 0 : 1;
+            s.aux = (!raw && L.noise) ? L.noise_dev : nullptr;
+            if (tc) {
+                s.kind = K_SEPCONV_TC;
+                s.in = L.down ? nullptr : in;  // down: A operand comes pre-split from K_DWDOWN
+                s.hi = ghi; s.lo = glo;
+                const char* err = migan::sepconv_tc_plan(&s.tc, path == MIGAN_PATH_TC_FAST ? 1 : 3, s.in, ghi, glo, L.w9, L.bias,
+                                                         L.pw_hi, L.pw_lo, L.tc_inv_scale, s.aux, pw_out, n, L.res_pw, L.cin, L.cout, s.act);
+                if (err) return fail(MIGAN_ERR_CUDA, "tcgen05 plan for %s failed: %s", L.p.c_str(), err);
+            } else {
+                s.kind = K_GEMM_SIMT; s.in = gemm_in;
+            }
+            set_tap(s, L.p + (raw ? "pw" : "out"), pw_out, L.cout, L.res_pw, L.res_pw);
+            steps.push_back(s);
+        }
+        out_ptr = pw_out; out_idx = pw_idx;
+        if (L.up) {
+            float* up_out; int up_idx;
+            if (out_fixed) { up_out = out_fixed; up_idx = -1; }
+            else { up_idx = other(pw_idx); up_out = S[up_idx]; }
+            Step s; s.kind = K_UP2; s.L = &L; s.in = pw_out; s.out = up_out; s.aux = skip;
+            s.n = n; s.H = L.res_pw; s.W = L.res_pw; s.C = L.cout;
+            set_tap(s, L.p + (skip ? "out_skip" : "out"), up_out, L.cout, L.res_out, L.res_out);
+            steps.push_back(s);
+            out_ptr = up_out; out_idx = up_idx;
+        } else if (skip) {
+            Step s; s.kind = K_ADD; s.out = pw_out; s.aux = skip; s.n = n; s.H = L.res_out; s.W = L.res_out; s.C = L.cout;
+            set_tap(s, L.p + "out_skip", pw_out, L.cout, L.res_out, L.res_out);
+            steps.push_back(s);
+        }
+        return MIGAN_OK;
+    }
+
+    int build() {
+        size_t off = 0;
+        for (int r : c->enc_res) { feat[r] = reinterpret_cast<float*>(base + off); off += feat_bytes(n, r); }
+        for (int i = 0; i < 3; ++i) { S[i] = reinterpret_cast<float*>(base + off); off += scratch_bytes(c, n); }
+        for (int i = 0; i < 2; ++i) { IMG[i] = reinterpret_cast<float*>(base + off); off += img_bytes(c, n); }
+        const int R = c->resolution;
+        // ---- encoder (migan_inference.py:235-246) ----
+        {
+            Step s; s.kind = K_STEM; s.io_flags = PTR_X; s.out = S[0]; s.n = n; s.H = R; s.W = R; s.C = channels(R);
+            set_tap(s, "encoder.b" + std::to_string(R) + ".fromrgb", S[0], channels(R), R, R);
+            steps.push_back(s);
+        }
+        const float* cur = S[0];
+        int cur_idx = 0;
+        for (size_t i = 0; i < c->enc_res.size(); ++i) {
+            const int r = c->enc_res[i];
+            int oi; float* op;
+            int rc = emit_sepconv(c->enc1[i], cur, cur_idx, feat[r], nullptr, oi, op);  // feat = conv1(x)
+            if (rc) return rc;
+            rc = emit_sepconv(c->enc2[i], feat[r], -1, nullptr, nullptr, oi, op);      // x = conv2(feat)
+            if (rc) return rc;
+            cur = op; cur_idx = oi;
+        }
+        // ---- synthesis (migan_inference.py:347-352) ----
+        int img_cur = -1;
+        for (size_t i = 0; i < c->syn_res.size(); ++i) {
+            const int r = c->syn_res[i];
+            int oi; float* op;
+            int rc = emit_sepconv(c->syn1[i], cur, cur_idx, nullptr, feat[r], oi, op);  // x = conv1(x) + enc_feat
+            if (rc) return rc;
+            cur = op; cur_idx = oi;
+            rc = emit_sepconv(c->syn2[i], cur, cur_idx, nullptr, nullptr, oi, op);
+            if (rc) return rc;
+            cur = op; cur_idx = oi;
+            const bool last = (i + 1 == c->syn_res.size());
+            Step s; s.kind = K_TORGB; s.T = &c->torgb[i]; s.in = cur; s.n = n; s.H = r; s.W = r; s.C = channels(r);
+            s.aux = (img_cur >= 0) ? IMG[img_cur] : nullptr;
+            const int img_next = (img_cur < 0) ? 0 : 1 - img_cur;
+            if (last) { s.io_flags = PTR_Y; s.out = nullptr; }
+            else s.out = IMG[img_next];
+            set_tap(s, c->torgb[i].p + "img", s.out, 3, r, r, true, last ? PTR_Y : 0);
+            steps.push_back(s);
+            img_cur = img_next;
+        }
+        return MIGAN_OK;
+    }
+};
+
+int build_plan(migan_ctx* ctx, int n, int path, void* ws) {
+    PlanBuilder pb;
+    pb.c = ctx; pb.n = n; pb.path = path; pb.base = static_cast<unsigned char*>(ws);
+    int rc = pb.build();
+    if (rc) return rc;
+    ctx->plan.n = n; ctx->plan.path = path; ctx->plan.ws = ws;
+    ctx->plan.steps.swap(pb.steps);
+    return MIGAN_OK;
+}
+
+int run_step(migan_ctx* ctx, const Step& s, const float* x, float* y, cudaStream_t st) {
+    const float* in = (s.io_flags & PTR_X) ? x : s.in;
+    float* out = (s.io_flags & PTR_Y) ? y : s.out;
+    cudaError_t e = cudaSuccess;
+    switch (s.kind) {
+        case K_STEM:
+            e = migan::launch_stem(in, ctx->fromrgb_w, ctx->fromrgb_b, out, s.n, s.H, s.W, s.C, st);
+            break;
+        case K_DW:
+            e = migan::launch_dw3x3(in, s.L->w9, s.L->bias, out, s.n, s.H, s.W, s.C, st);
+            break;
+        case K_DWDOWN:
+            e = migan::launch_dw3x3_down(in, s.L->w9, s.L->bias, s.L->fir16, s.out, s.hi, s.lo, s.n, s.H, s.W, s.C, st);
+            break;
+        case K_GEMM_SIMT:
+            e = migan::launch_pw_gemm_simt(in, s.L->pw_t, out, (int64_t)s.n * s.H * s.W, s.L->cin, s.L->cout,
+                                           s.aux, s.H * s.W, s.act, st);
+            break;
+        case K_SEPCONV_TC:
+            e = migan::launch_sepconv_tc(s.tc, st);
+            break;
+        case K_UP2:
+            e = migan::launch_up2(in, s.L->fir16, s.L->noise ? s.L->noise_dev : nullptr, s.aux, out, s.n, s.H, s.W, s.C, st);
+            break;
+        case K_TORGB:
+            e = migan::launch_torgb(in, s.T->w, s.T->b, s.aux, s.T->fir, out, s.n, s.H, s.C, st);
+            break;
+        case K_ADD:
+            e = migan::launch_add(out, s.aux, (int64_t)s.n * s.H * s.W * s.C, st);
+            break;
+    }
+    if (e != cudaSuccess) return fail(MIGAN_ERR_CUDA, "kernel launch (step kind %d, %s) failed: %s", (int)s.kind,
+                                      s.tap.c_str(), cudaGetErrorString(e));
+    ctx->last_launches++;
+    if (ctx->tap_dst && !s.tap.empty() && s.tap == ctx->tap_name) {
+        const float* src = (s.tap_flags & PTR_Y) ? y : s.tap_src;
+        if (s.tap_planar)
+            e = cudaMemcpyAsync(ctx->tap_dst, src, sizeof(float) * (size_t)s.n * s.tapC * s.tapH * s.tapW, cudaMemcpyDeviceToDevice, st);
+        else
+            e = migan::launch_nhwc_to_nchw(src, ctx->tap_dst, s.n, s.tapH, s.tapW, s.tapC, st);
+        if (e != cudaSuccess) return fail(MIGAN_ERR_CUDA, "tap copy failed: %s", cudaGetErrorString(e));
+    }
+    return MIGAN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int migan_forward(migan_ctx* ctx, const float* x, float* y, int n, void* workspace, size_t workspace_bytes,
+                  int path, void* stream) {
+    if (!ctx || !x || !y || !workspace) return fail(MIGAN_ERR_INVALID, "null argument");
+    if (!ctx->finalized) return fail(MIGAN_ERR_STATE, "weights not finalized (call migan_finalize_weights)");
+    if (n <= 0) return fail(MIGAN_ERR_INVALID, "batch size must be positive, got %d", n);
+    if (path != MIGAN_PATH_SIMT && path != MIGAN_PATH_TC && path != MIGAN_PATH_TC_FAST)
+        return fail(MIGAN_ERR_INVALID, "unknown path %d", path);
+    if (workspace_bytes < migan_workspace_bytes(ctx, n))
+        return fail(MIGAN_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, migan_workspace_bytes(ctx, n));
+    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
+        return fail(MIGAN_ERR_WORKSPACE, "workspace must be 1024-byte aligned, x / y 16-byte aligned");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->plan.n != n || ctx->plan.path != path || ctx->plan.ws != workspace) {
+        int rc = build_plan(ctx, n, path, workspace);
+        if (rc) return rc;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ctx->last_launches = 0;
+    for (const Step& s : ctx->plan.steps) {
+        int rc = run_step(ctx, s, x, y, st);
+        if (rc) return rc;
+    }
+    return MIGAN_OK;
+}
+
+int migan_forward_host(migan_ctx* ctx, const float* x_host, float* y_host, int n, void* workspace,
+                       size_t workspace_bytes, int path, void* stream) {
+    if (!ctx || !x_host || !y_host || !workspace) return fail(MIGAN_ERR_INVALID, "null argument");
+    if (n <= 0) return fail(MIGAN_ERR_INVALID, "batch size must be positive, got %d", n);
+    const size_t ws = migan_workspace_bytes(ctx, n);
+    if (workspace_bytes < ws + migan_host_staging_bytes(ctx, n))
+        return fail(MIGAN_ERR_WORKSPACE, "workspace too small for host staging: %zu < %zu bytes", workspace_bytes,
+                    ws + migan_host_staging_bytes(ctx, n));
+    const size_t px = (size_t)n * ctx->resolution * ctx->resolution * sizeof(float);
+    float* xd = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + ws);
+    float* yd = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + ws + align_up(4 * px, 1024));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(xd, x_host, 4 * px, cudaMemcpyHostToDevice, st));
+    int rc = migan_forward(ctx, xd, yd, n, workspace, ws, path, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(y_host, yd, 3 * px, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MIGAN_OK;
+}
+
+int migan_last_launch_count(const migan_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+int migan_set_tap(migan_ctx* ctx, const char* name, float* dst) {
+    if (!ctx) return fail(MIGAN_ERR_INVALID, "null ctx");
+    if (!name) { ctx->tap_name.clear(); ctx->tap_dst = nullptr; return MIGAN_OK; }
+    ctx->tap_name = name;
+    ctx->tap_dst = dst;
+    return MIGAN_OK;
+}
+
+int migan_tap_info(const migan_ctx* ctx, int path, int index, const char** name, int shape[3]) {
+    if (!ctx) return fail(MIGAN_ERR_INVALID, "null ctx");
+    // Build a throw-away plan for n = 1 on a fake base (no kernels are launched; tc plans need
+    // finalized weights only for pointers, which are not dereferenced here).
+    static thread_local std::vector<Step> cache;
+    static thread_local const migan_ctx* cache_ctx = nullptr;
+    static thread_local int cache_path = -1;
+    if (cache_ctx != ctx || cache_path != path) {
+        PlanBuilder pb;
+        // Enumerate with the CUDA-core builder (no tensor maps needed); the tensor-core paths fuse
+        // the depthwise / FIR-down stages away, so their taps are filtered out below.
+        pb.c = const_cast<migan_ctx*>(ctx); pb.n = 1; pb.path = MIGAN_PATH_SIMT;
+        pb.base = reinterpret_cast<unsigned char*>(uintptr_t(1) << 20);
+        if (pb.build()) return MIGAN_ERR_INVALID;
+        cache.clear();
+        for (Step& s : pb.steps) {
+            if (s.tap.empty()) continue;
+            if (path != MIGAN_PATH_SIMT) {
+                const std::string& t = s.tap;
+                auto ends = [&](const char* suf) { size_t l = strlen(suf); return t.size() >= l && t.compare(t.size() - l, l, suf) == 0; };
+                if (ends(".dw_act") || ends(".down")) continue;
+            }
+            cache.push_back(s);
+        }
+        cache_ctx = ctx; cache_path = path;
+    }
+    if (index < 0 || index >= (int)cache.size()) return MIGAN_ERR_INVALID;
+    if (name) *name = cache[index].tap.c_str();
+    if (shape) { shape[0] = cache[index].tapC; shape[1] = cache[index].tapH; shape[2] = cache[index].tapW; }
+    return MIGAN_OK;
+}
+
+int b200_upfirdn2d(const float* x, const float* f, float* y, int n, int c, int h, int w, int fh, int fw,
+                   int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1,
+                   int flip_filter, float gain, void* stream) {
+    if (!x || !y) return fail(MIGAN_ERR_INVALID, "null tensor");
+    if (n < 0 || c < 0 || h < 1 || w < 1) return fail(MIGAN_ERR_INVALID, "bad input shape [%d,%d,%d,%d]", n, c, h, w);
+    if (upx < 1 || upy < 1 || downx < 1 || downy < 1) return fail(MIGAN_ERR_INVALID, "up/down factors must be >= 1");
+    static const float one = 1.0f;
+    static thread_local float* d_one = nullptr;
+    if (!f) {
+        if (!d_one) {
+            CUDA_TRY(cudaMalloc(&d_one, sizeof(float)));
+            CUDA_TRY(cudaMemcpy(d_one, &one, sizeof(float), cudaMemcpyHostToDevice));
+        }
+        f = d_one; fh = 1; fw = 1;
+    }
+    if (fh < 1 || fw < 1 || fh * fw > 1024) return fail(MIGAN_ERR_INVALID, "filter must have 1..1024 taps, got %dx%d", fh, fw);
+    const int ow = (w * upx + padx0 + padx1 - fw + downx) / downx;  // upfirdn2d.cpp:32-33
+    const int oh = (h * upy + pady0 + pady1 - fh + downy) / downy;
+    if (ow < 1 || oh < 1) return fail(MIGAN_ERR_INVALID, "output size must be >= 1, got %dx%d", oh, ow);
+    cudaError_t e = migan::launch_upfirdn2d(x, f, y, n, c, h, w, fh, fw, upx, upy, downx, downy, padx0, padx1, pady0, pady1,
+                                            flip_filter, gain, oh, ow, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(MIGAN_ERR_CUDA, "upfirdn2d launch failed: %s", cudaGetErrorString(e));
+    return MIGAN_OK;
+}
+
+int b200_bias_act(const float* x, const float* b, float* y, int64_t numel, int64_t step_b, int size_b,
+                  int act, float alpha, float gain, float clamp, void* stream) {
+    if (numel < 0 || (numel > 0 && (!x || !y))) return fail(MIGAN_ERR_INVALID, "null tensor");
+    if (act < 1 || act > 9) return fail(MIGAN_ERR_INVALID, "act must be in 1..9, got %d", act);
+    if (b && (step_b < 1 || size_b < 1)) return fail(MIGAN_ERR_INVALID, "bad bias stride/size");
+    cudaError_t e = migan::launch_bias_act(x, b, y, numel, step_b, size_b, act, alpha, gain, clamp, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(MIGAN_ERR_CUDA, "bias_act launch failed: %s", cudaGetErrorString(e));
+    return MIGAN_OK;
+}
+
+}  // extern "C"

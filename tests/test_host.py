@@ -1,0 +1,98 @@
+"""Host-side logic and the C-ABI surface, no GPU needed."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import migan_b200
+from migan_b200 import _abi, arch
+from oracle import migan_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "migan_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b((?:migan|b200)_[a-z0-9_]+)\s*\(", header))
+    bound = {name for name, _, _ in _abi.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    for name in declared:
+        assert hasattr(lib, name)
+    assert b"sm_100a" in lib.migan_version()
+
+
+@pytest.mark.parametrize("R", [8, 64, 256, 512])
+def test_state_dict_layout_matches_reference_order(lib, R):
+    """Python module, C registry and the oracle spec (checked against the real reference by
+    make_golden.py with strict=True) all agree on names, order and shapes."""
+    spec = O.state_dict_spec(R)
+    g = migan_b200.Generator(R)
+    sd = g.state_dict()
+    assert list(sd.keys()) == list(spec.keys())
+    assert all(tuple(sd[k].shape) == tuple(spec[k]) for k in spec)
+    h = ctypes.c_void_p()
+    _abi.check(lib.migan_create(R, -1, ctypes.byref(h)))
+    try:
+        assert lib.migan_num_weights(h) == len(spec)
+        for i, (k, shape) in enumerate(spec.items()):
+            nm, nd, sh = ctypes.c_char_p(), ctypes.c_int(), (ctypes.c_int64 * 4)()
+            _abi.check(lib.migan_weight_info(h, i, ctypes.byref(nm), ctypes.byref(nd), sh))
+            assert nm.value.decode() == k and tuple(sh[: nd.value]) == tuple(shape)
+        assert lib.migan_workspace_bytes(h, 2) > lib.migan_workspace_bytes(h, 1) > 0
+    finally:
+        lib.migan_destroy(h)
+
+
+def test_param_vs_buffer_split_and_attribute_paths():
+    g = migan_b200.Generator(256)
+    assert sum(p.numel() for p in g.parameters()) == 5943617
+    bufs = dict(g.named_buffers())
+    assert "synthesis.b64.conv1.noise_const" in bufs and "synthesis.b64.upsample.filter_const" in bufs
+    assert g.encoder.b256.fromrgb.weight.shape == (128, 4, 1, 1)
+    assert g.synthesis.b8.conv1.use_noise and not g.synthesis.b4.conv2.use_noise
+    assert g.encoder.b64.conv2.downsample.filter.weight.shape == (512, 1, 4, 4)
+    # a reference state_dict (seeded stand-in) loads strictly
+    g.load_state_dict(O.make_state_dict(256), strict=True)
+
+
+def test_constructor_and_cpu_errors(lib):
+    with pytest.raises(ValueError):
+        migan_b200.Generator(96)          # reference raises ValueError (migan_inference.py:215-216)
+    g = migan_b200.Generator(64)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        g(torch.zeros(1, 4, 64, 64))
+    h = ctypes.c_void_p()
+    assert lib.migan_create(96, -1, ctypes.byref(h)) == _abi.ERR_INVALID
+    assert b"power of two" in lib.migan_last_error()
+    _abi.check(lib.migan_create(64, -1, ctypes.byref(h)))
+    w = torch.zeros(7)
+    assert lib.migan_set_weight(h, b"no.such.key", w.data_ptr(), 7) == _abi.ERR_INVALID
+    assert lib.migan_set_weight(h, b"encoder.b64.fromrgb.bias", w.data_ptr(), 7) == _abi.ERR_INVALID
+    assert lib.migan_finalize_weights(h) == _abi.ERR_CUDA        # description-only context cannot compute
+    lib.migan_destroy(h)
+
+
+def test_no_cuda_device_fails_loudly(lib):
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = ctypes.c_void_p()
+    assert lib.migan_create(64, 0, ctypes.byref(h)) == _abi.ERR_CUDA
+    assert b"no CPU path" in lib.migan_last_error()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "mi-gan_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_arch_helpers():
+    assert arch.encoder_resolutions(256) == [256, 128, 64, 32, 16, 8, 4]
+    assert arch.synthesis_resolutions(64) == [4, 8, 16, 32, 64]
+    assert [arch.nf(r) for r in (512, 256, 128, 64, 4)] == [64, 128, 256, 512, 512]
