@@ -1,11 +1,585 @@
-// placeholder until the tcgen05 kernel lands
-#include "sepconv_tc.h"
+// Fused SeparableConv2d on Blackwell tensor cores (sm_100a): the hot kernel of the generator.
+//
+//   out = epi( PW( act( DW3x3(in) + b ) ) )          lib/model_zoo/migan_inference.py:154-170
+//
+//   DW3x3 + bias + lrelu_agc   CUDA cores, fp32, on a TMA-staged NHWC tile + 1-pixel halo
+//   PW (1x1 conv, Cin -> Cout) tcgen05.mma kind::f16, M=128 pixels x N<=128 channels per CTA,
+//                              accumulators in TMEM.  fp32-faithful mode: both operands are split
+//                              into fp16 (hi, lo) pairs and  Ah*Bh + Al*Bh + Ah*Bl  is accumulated
+//                              in fp32 (3 passes); fast mode: Ah*Bh only.
+//   epi                        TMEM -> registers: * 2^-k, + noise, lrelu_agc -> swizzled smem
+//                              -> TMA store (NHWC fp32)
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   input chunks (32 channels, fp32, halo'd) and weight K-blocks
+//   warp 1      MMA issuer     one elected lane issues tcgen05.mma / tcgen05.commit; owns TMEM
+//   warps 2-5   epilogue       one TMEM lane quarter each
+//   warps 6-13  prologue       depthwise conv -> fp16 hi/lo A operand in UMMA K-major SW128 layout
+// All hand-offs are mbarrier pipelines (input ring, A ring, B ring, TMEM accumulator ring).
+//
+// Two A-operand sources:
+//   A_DW  (mode 0) prologue as above (plain layers and the 1x1 of up-sampling layers)
+//   A_TMA (mode 1) the operand was already produced as fp16 hi/lo by dw3x3_down_kernel
+//                  (down-sampling layers); TMA loads it straight into the A ring.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
 #include "kernels.h"
+#include "sepconv_tc.h"
+
 namespace migan {
-cudaError_t configure_sepconv_tc() { return cudaSuccess; }
-const char* sepconv_tc_plan(SepconvTcArgs*, int, const float*, const __half*, const __half*, const float*, const float*,
-                            const __half*, const __half*, float, const float*, float*, int, int, int, int, int) {
-    return "tcgen05 path not built";
+
+namespace {
+
+constexpr int kThreads = 448;
+constexpr int kProWarp0 = 6;       // first prologue warp
+constexpr int kNumProWarps = 8;
+constexpr int kEpiWarp0 = 2;
+constexpr int kTileM = 128;
+constexpr int kKBlock = 64;        // channels per A/B stage (128 bytes of fp16: one SW128 row)
+constexpr int kChunkC = 32;        // channels per input chunk (128 bytes of fp32)
+constexpr uint32_t kABytes = kTileM * kKBlock * 2;   // 16 KB per hi or lo
+constexpr uint32_t kAStage = 2 * kABytes;            // hi + lo
+constexpr uint32_t kEpiBuf = kTileM * 32 * 4;        // 16 KB: 128 rows x 32 fp32
+constexpr int kMaxStages = 8;   // input / B ring slots (A ring: <= 4)
+constexpr uint32_t kSmemLimit = 232448;              // 227 KB
+
+struct Params {
+    CUtensorMap map_in, map_a_hi, map_a_lo, map_w_hi, map_w_lo, map_out;
+    const float* w9;
+    const float* bias;
+    const float* noise;
+    float inv_scale;
+    int n, H, W, cin, cout;
+    int act, passes, a_mode;
+    int tile_n, tile_h, tile_w, n_tile;      // n_tile = N per CTA tile (64 or 128)
+    int tiles_x, tiles_y, tiles_n, num_n_tiles, num_tiles;
+    int num_kb;                               // cin / 64
+    int in_stages, a_stages, b_stages, b_resident;
+    uint32_t in_chunk_bytes;                  // tile_n*(tile_h+2)*(tile_w+2)*128
+    uint32_t in_stage_stride;                 // rounded to 1024
+    uint32_t off_in, off_a, off_b, off_epi;   // smem offsets from the 1024-aligned base
+    int* error_flag;
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-cudaError_t launch_sepconv_tc(const SepconvTcArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must never hang the GPU -- report and trap instead.
+__device__ __noinline__ void mbar_timeout(int code, uint32_t parity, int* error_flag) {
+    if (error_flag) atomicExch(error_flag, code);
+    printf("[sepconv_tc] mbarrier timeout: code=%d parity=%u block=%d thread=%d\n", code, parity, blockIdx.x, threadIdx.x);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code, int* error_flag) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) mbar_timeout(code, parity, error_flag);
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, rows of 64 fp16 (128 B),
+// 8-row groups 1024 B apart (SBO).  Bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address  [0,14)
+    d |= (uint64_t)1 << 16;                              // LBO (unused for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                    // SBO = 1024 B   [32,46)
+    d |= (uint64_t)1 << 46;                              // descriptor version 1 (sm_100)
+    d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor (InstrDescriptor in the same header): D=f32, A=B=f16, K-major both, M=128.
+__device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+struct TileCoord {
+    int n0, y0, x0, nt;   // first image / row / column of the M tile, N-tile index
+};
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
+    TileCoord c;
+    c.nt = tile % p.num_n_tiles;
+    int m = tile / p.num_n_tiles;
+    c.x0 = (m % p.tiles_x) * p.tile_w;
+    m /= p.tiles_x;
+    c.y0 = (m % p.tiles_y) * p.tile_h;
+    c.n0 = (m / p.tiles_y) * p.tile_n;
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+sepconv_tc_kernel(const __grid_constant__ Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    // mbarriers: [0,8) full_in  [8,16) empty_in  [16,20) full_a  [20,24) empty_a
+    //            [24,32) full_b  [32,40) empty_b  [40,42) full_acc  [42,44) empty_acc
+    __shared__ __align__(8) uint64_t bars[44];
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_in = [&](int s) { return bar0 + 8u * (0 + s); };
+    auto empty_in = [&](int s) { return bar0 + 8u * (8 + s); };
+    auto full_a = [&](int s) { return bar0 + 8u * (16 + s); };
+    auto empty_a = [&](int s) { return bar0 + 8u * (20 + s); };
+    auto full_b = [&](int s) { return bar0 + 8u * (24 + s); };
+    auto empty_b2 = [&](int s) { return bar0 + 8u * (32 + s); };
+    auto full_acc = [&](int s) { return bar0 + 8u * (40 + s); };
+    auto empty_acc = [&](int s) { return bar0 + 8u * (42 + s); };
+
+    const int a_dw = (p.a_mode == 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.in_stages; ++s) { mbar_init(full_in(s), 1); mbar_init(empty_in(s), kNumProWarps / 2); }
+        for (int s = 0; s < p.a_stages; ++s) { mbar_init(full_a(s), a_dw ? kNumProWarps : 1); mbar_init(empty_a(s), 1); }
+        for (int s = 0; s < p.b_stages; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b2(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(full_acc(s), 1); mbar_init(empty_acc(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        if (a_dw) prefetch_tensormap(&p.map_in); else { prefetch_tensormap(&p.map_a_hi); prefetch_tensormap(&p.map_a_lo); }
+        prefetch_tensormap(&p.map_w_hi); prefetch_tensormap(&p.map_w_lo); prefetch_tensormap(&p.map_out);
+    }
+    if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM by construction)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const int num_kb = p.num_kb;
+    const int my_tiles = (p.num_tiles > (int)blockIdx.x) ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            const uint32_t b_stage_bytes = (uint32_t)p.n_tile * kKBlock * 2 * 2;   // hi + lo
+            for (int it = 0; it < my_tiles; ++it) {
+                const TileCoord tc = decode_tile(p, blockIdx.x + it * gridDim.x);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int kbc = it * num_kb + kb;
+                    if (a_dw) {
+                        for (int g = 0; g < 2; ++g) {
+                            const int cc = 2 * kbc + g;
+                            const int s = cc % p.in_stages;
+                            mbar_wait(empty_in(s), ((cc / p.in_stages) & 1) ^ 1, 100 + s, p.error_flag);
+                            mbar_expect_tx(full_in(s), p.in_chunk_bytes);
+                            tma_load_4d(smem_base + p.off_in + s * p.in_stage_stride, &p.map_in, full_in(s),
+                                        kb * kKBlock + g * kChunkC, tc.x0 - 1, tc.y0 - 1, tc.n0);
+                        }
+                    } else {
+                        const int s = kbc % p.a_stages;
+                        mbar_wait(empty_a(s), ((kbc / p.a_stages) & 1) ^ 1, 110 + s, p.error_flag);
+                        mbar_expect_tx(full_a(s), kAStage);
+                        const int row0 = (blockIdx.x + it * gridDim.x) / p.num_n_tiles * kTileM;
+                        tma_load_2d(smem_base + p.off_a + s * kAStage, &p.map_a_hi, full_a(s), kb * kKBlock, row0);
+                        tma_load_2d(smem_base + p.off_a + s * kAStage + kABytes, &p.map_a_lo, full_a(s), kb * kKBlock, row0);
+                    }
+                    if (!p.b_resident || it == 0) {
+                        const int s = p.b_resident ? kb : kbc % p.b_stages;
+                        if (!p.b_resident) mbar_wait(empty_b2(s), ((kbc / p.b_stages) & 1) ^ 1, 120 + s, p.error_flag);
+                        mbar_expect_tx(full_b(s), b_stage_bytes);
+                        const uint32_t dst = smem_base + p.off_b + s * b_stage_bytes;
+                        tma_load_2d(dst, &p.map_w_hi, full_b(s), kb * kKBlock, tc.nt * p.n_tile);
+                        tma_load_2d(dst + b_stage_bytes / 2, &p.map_w_lo, full_b(s), kb * kKBlock, tc.nt * p.n_tile);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        const uint32_t idesc = umma_idesc_f16(p.n_tile);
+        const uint32_t b_stage_bytes = (uint32_t)p.n_tile * kKBlock * 2 * 2;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int acc = it & 1;
+            mbar_wait(empty_acc(acc), ((it >> 1) & 1) ^ 1, 200 + acc, p.error_flag);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.n_tile);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int kbc = it * num_kb + kb;
+                const int sa = kbc % p.a_stages;
+                const int sb = p.b_resident ? kb : kbc % p.b_stages;
+                mbar_wait(full_a(sa), (kbc / p.a_stages) & 1, 210 + sa, p.error_flag);
+                mbar_wait(full_b(sb), p.b_resident ? 0 : (kbc / p.b_stages) & 1, 220 + sb, p.error_flag);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_base + p.off_a + sa * kAStage, a_lo = a_hi + kABytes;
+                    const uint32_t b_hi = smem_base + p.off_b + sb * b_stage_bytes, b_lo = b_hi + b_stage_bytes / 2;
+                    const uint64_t dah = umma_desc_sw128(a_hi), dal = umma_desc_sw128(a_lo);
+                    const uint64_t dbh = umma_desc_sw128(b_hi), dbl = umma_desc_sw128(b_lo);
+#pragma unroll
+                    for (int k = 0; k < kKBlock / 16; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 16 fp16 = 32 bytes along K inside the SW128 row
+                        tc_mma_f16(tmem_d, dah + adv, dbh + adv, idesc, (kb | k) != 0);
+                        if (p.passes == 3) {
+                            tc_mma_f16(tmem_d, dal + adv, dbh + adv, idesc, 1u);
+                            tc_mma_f16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+                        }
+                    }
+                    tc_commit(empty_a(sa));                       // A slot reusable once these MMAs retire
+                    if (!p.b_resident) tc_commit(empty_b2(sb));
+                    if (kb == num_kb - 1) tc_commit(full_acc(acc));  // accumulator complete
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < kProWarp0) {
+        // ================================ epilogue ====================================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;               // pixel row of the M tile
+        const int hw = p.tile_h * p.tile_w;
+        const int img_l = row / hw, yl = (row / p.tile_w) % p.tile_h, xl = row % p.tile_w;
+        const bool issuer = (threadIdx.x == kEpiWarp0 * 32);
+        const int chunks = p.n_tile / 32;
+        int buf = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const TileCoord tc = decode_tile(p, blockIdx.x + it * gridDim.x);
+            const int acc = it & 1;
+            mbar_wait(full_acc(acc), (it >> 1) & 1, 300 + acc, p.error_flag);
+            tc_fence_after();
+            float nz = 0.f;
+            if (p.noise) nz = __ldg(p.noise + (tc.y0 + yl) * p.W + tc.x0 + xl);
+            for (int j = 0; j < chunks; ++j) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_tile + j * 32), v);
+                tc_wait_ld();
+                if (j == chunks - 1) {               // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty_acc(acc));
+                }
+                float o[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float f = __uint_as_float(v[i]) * p.inv_scale + nz;
+                    o[i] = p.act ? lrelu_agc(f) : f;
+                }
+                // staging buffer `buf` must have been drained by the TMA store issued two chunks ago
+                if (issuer) tma_wait_group_read<1>();
+                named_bar_sync(1, 128);
+                const uint32_t dst = smem_base + p.off_epi + buf * kEpiBuf + row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t a = dst + (((uint32_t)c ^ (uint32_t)(row & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(o[4 * c]), "f"(o[4 * c + 1]),
+                                 "f"(o[4 * c + 2]), "f"(o[4 * c + 3]) : "memory");
+                }
+                fence_proxy_async();
+                named_bar_sync(1, 128);
+                if (issuer) {
+                    tma_store_4d(&p.map_out, smem_base + p.off_epi + buf * kEpiBuf, tc.nt * p.n_tile + j * 32, tc.x0, tc.y0, tc.n0);
+                    tma_commit_group();
+                }
+                buf ^= 1;
+            }
+        }
+        if (issuer) tma_wait_group_all();
+        (void)img_l;
+    } else if (a_dw) {
+        // ================================ prologue (depthwise) ========================
+        const int g = (warp - kProWarp0) >> 2;            // channel half of the K-block this group produces
+        const int tg = threadIdx.x - (kProWarp0 * 32 + g * 128);
+        const int ncols = p.tile_n * p.tile_w;
+        const int th = p.tile_h, tw = p.tile_w;
+        const int row_f4 = (tw + 2) * 8;                  // float4 per halo'd input row (32 ch = 8 float4 / pixel)
+        for (int it = 0; it < my_tiles; ++it) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int kbc = it * num_kb + kb;
+                const int cc = 2 * kbc + g;
+                const int s = cc % p.in_stages;
+                const int sa = kbc % p.a_stages;
+                mbar_wait(full_in(s), (cc / p.in_stages) & 1, 400 + s, p.error_flag);
+                mbar_wait(empty_a(sa), ((kbc / p.a_stages) & 1) ^ 1, 410 + sa, p.error_flag);
+                const float4* sin = reinterpret_cast<const float4*>(smem_gen + p.off_in + s * p.in_stage_stride);
+                uint8_t* a_hi = smem_gen + p.off_a + sa * kAStage;
+                uint8_t* a_lo = a_hi + kABytes;
+                for (int item = tg; item < ncols * 8; item += 128) {
+                    const int cvec = item & 7, colidx = item >> 3;
+                    const int col = (colidx & 3) * (ncols >> 2) + (colidx >> 2);
+                    const int img_l = col / tw, x = col - img_l * tw;
+                    const int cg = kb * kKBlock + g * kChunkC + cvec * 4;
+                    float4 w[9];
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) w[t] = ldg4(p.w9 + t * p.cin + cg);
+                    const float4 bv = ldg4(p.bias + cg);
+                    const float4* base = sin + (img_l * (th + 2) * (tw + 2) + x) * 8 + cvec;
+                    float4 r0[3], r1[3], r2[3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { r0[d] = base[d * 8]; r1[d] = base[row_f4 + d * 8]; }
+                    const uint32_t jchunk = (uint32_t)(g * 4 + (cvec >> 1));
+                    const uint32_t sub = (uint32_t)(cvec & 1) * 8;
+                    for (int y = 0; y < th; ++y) {
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) r2[d] = base[(y + 2) * row_f4 + d * 8];
+                        float4 a = bv;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) { fma4(a, w[d], r0[d]); fma4(a, w[3 + d], r1[d]); fma4(a, w[6 + d], r2[d]); }
+                        a = lrelu_agc4(a);
+                        __half h[4], l[4];
+                        split_f16(a.x, kActSplitScale, h[0], l[0]);
+                        split_f16(a.y, kActSplitScale, h[1], l[1]);
+                        split_f16(a.z, kActSplitScale, h[2], l[2]);
+                        split_f16(a.w, kActSplitScale, h[3], l[3]);
+                        const int m = (img_l * th + y) * tw + x;
+                        const uint32_t off = (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u + ((jchunk ^ (uint32_t)(m & 7)) << 4) + sub;
+                        *reinterpret_cast<uint2*>(a_hi + off) = *reinterpret_cast<uint2*>(h);
+                        *reinterpret_cast<uint2*>(a_lo + off) = *reinterpret_cast<uint2*>(l);
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) { r0[d] = r1[d]; r1[d] = r2[d]; }
+                    }
+                }
+                fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(full_a(sa));
+                    mbar_arrive(empty_in(s));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+const char* encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* addr, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return "cuTensorMapEncodeTiled entry point not available";
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(addr), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        static thread_local char msg[96];
+        snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return msg;
+    }
+    return nullptr;
+}
+
+int* g_error_flag = nullptr;   // device int, per process (debug aid for bounded waits)
+
+}  // namespace
+
+// Params is kept opaque to the ABI layer: SepconvTcArgs carries it as bytes.
+static_assert(sizeof(Params) <= sizeof(((SepconvTcArgs*)0)->params_blob), "params blob too small");
+
+cudaError_t configure_sepconv_tc() {
+    cudaError_t e = cudaFuncSetAttribute(sepconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit - 4096);
+    if (e != cudaSuccess) return e;
+    if (!g_error_flag) {
+        e = cudaMalloc(&g_error_flag, sizeof(int));
+        if (e != cudaSuccess) return e;
+        e = cudaMemset(g_error_flag, 0, sizeof(int));
+    }
+    return e;
+}
+
+const char* sepconv_tc_plan(SepconvTcArgs* args, int passes, const float* in_f32, const __half* a_hi, const __half* a_lo,
+                            const float* w9, const float* bias, const __half* w_hi, const __half* w_lo,
+                            float inv_scale, const float* noise, float* out, int n, int res, int cin, int cout, int act) {
+    Params p;
+    memset(&p, 0, sizeof(p));
+    if (cin % kKBlock != 0 || cout % 64 != 0) return "cin must be a multiple of 64 and cout of 64";
+    if (res < 4 || (res & (res - 1))) return "resolution must be a power of two >= 4";
+    p.a_mode = in_f32 ? 0 : 1;
+    if (!in_f32 && !(a_hi && a_lo)) return "no A operand";
+    p.w9 = w9; p.bias = bias; p.noise = noise; p.inv_scale = inv_scale;
+    p.n = n; p.H = res; p.W = res; p.cin = cin; p.cout = cout; p.act = act; p.passes = passes;
+    p.n_tile = (cout == 64) ? 64 : 128;
+    p.num_n_tiles = cout / p.n_tile;
+    p.num_kb = cin / kKBlock;
+    if (p.a_mode == 0) {   // spatial tiles with halo
+        p.tile_w = res >= 16 ? 16 : res;
+        p.tile_h = res >= 8 ? 8 : res;
+    } else {               // linear tiles (rows of the [P][cin] operand) expressed as a 4-D box for the store
+        p.tile_w = res >= 128 ? 128 : res;
+        p.tile_h = std::min(res, kTileM / p.tile_w);
+    }
+    p.tile_n = kTileM / (p.tile_w * p.tile_h);
+    p.tiles_x = res / p.tile_w; p.tiles_y = res / p.tile_h; p.tiles_n = (n + p.tile_n - 1) / p.tile_n;
+    p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.num_n_tiles;
+    p.in_chunk_bytes = (uint32_t)(p.tile_n * (p.tile_h + 2) * (p.tile_w + 2) * kChunkC * 4);
+    p.in_stage_stride = (p.in_chunk_bytes + 1023u) & ~1023u;
+
+    // ---- shared-memory budget -> stage counts ----
+    const uint32_t b_stage = (uint32_t)p.n_tile * kKBlock * 2 * 2;
+    const uint32_t budget = kSmemLimit - 4096 - 1024;   // static smem + alignment slack
+    const uint32_t epi = 2 * kEpiBuf;
+    p.b_resident = (p.num_n_tiles == 1 && (uint32_t)p.num_kb * b_stage <= 65536) ? 1 : 0;
+    p.b_stages = p.b_resident ? p.num_kb : 2;
+    p.a_stages = (p.a_mode == 0) ? 2 : 3;
+    uint32_t fixed = epi + p.a_stages * kAStage + p.b_stages * b_stage;
+    if (p.a_mode == 0) {
+        if (fixed + 2 * p.in_stage_stride > budget) return "shared memory budget exceeded";
+        p.in_stages = std::min<int>(kMaxStages, (budget - fixed) / p.in_stage_stride);
+        p.in_stages = std::min(p.in_stages, 6);
+    } else {
+        p.in_stages = 0;
+        if (fixed > budget) return "shared memory budget exceeded";
+    }
+    p.off_in = 0;
+    p.off_a = p.in_stages * p.in_stage_stride;
+    p.off_b = p.off_a + p.a_stages * kAStage;
+    p.off_epi = p.off_b + p.b_stages * b_stage;
+    const uint32_t smem_bytes = p.off_epi + epi + 1024;
+    if (smem_bytes > kSmemLimit - 4096) return "shared memory budget exceeded (layout)";
+    p.error_flag = g_error_flag;
+
+    // ---- tensor maps ----
+    const char* err = nullptr;
+    const uint64_t P = (uint64_t)n * res * res;
+    if (p.a_mode == 0) {
+        const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)res, (uint64_t)res, (uint64_t)n};
+        const uint64_t str[3] = {(uint64_t)cin * 4, (uint64_t)res * cin * 4, (uint64_t)res * res * cin * 4};
+        const uint32_t box[4] = {(uint32_t)kChunkC, (uint32_t)p.tile_w + 2, (uint32_t)p.tile_h + 2, (uint32_t)p.tile_n};
+        if ((err = encode_map(&p.map_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in_f32, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))) return err;
+    } else {
+        const uint64_t dims[2] = {(uint64_t)cin, P};
+        const uint64_t str[1] = {(uint64_t)cin * 2};
+        const uint32_t box[2] = {(uint32_t)kKBlock, (uint32_t)kTileM};
+        if ((err = encode_map(&p.map_a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a_hi, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return err;
+        if ((err = encode_map(&p.map_a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a_lo, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return err;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)cin, (uint64_t)cout};
+        const uint64_t str[1] = {(uint64_t)cin * 2};
+        const uint32_t box[2] = {(uint32_t)kKBlock, (uint32_t)p.n_tile};
+        if ((err = encode_map(&p.map_w_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_hi, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return err;
+        if ((err = encode_map(&p.map_w_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_lo, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return err;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)res, (uint64_t)res, (uint64_t)n};
+        const uint64_t str[3] = {(uint64_t)cout * 4, (uint64_t)res * cout * 4, (uint64_t)res * res * cout * 4};
+        const uint32_t box[4] = {32u, (uint32_t)p.tile_w, (uint32_t)p.tile_h, (uint32_t)p.tile_n};
+        if ((err = encode_map(&p.map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return err;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    args->grid = (unsigned)std::min(p.num_tiles, sms);
+    args->smem_bytes = smem_bytes;
+    args->num_tiles = p.num_tiles;
+    memcpy(args->params_blob, &p, sizeof(p));
+    return nullptr;
+}
+
+cudaError_t launch_sepconv_tc(const SepconvTcArgs& a, cudaStream_t s) {
+    Params p;
+    memcpy(&p, a.params_blob, sizeof(p));
+    sepconv_tc_kernel<<<a.grid, kThreads, a.smem_bytes, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace migan
