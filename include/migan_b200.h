@@ -80,6 +80,15 @@ int migan_forward_host(migan_ctx* ctx, const float* x_host, float* y_host, int n
 /* Kernels launched by the most recent migan_forward on this context. */
 int migan_last_launch_count(const migan_ctx* ctx);
 
+/* Per-launch timing for roofline reports: when enabled, every kernel launch of subsequent
+ * forwards is bracketed by cudaEvents on the launching stream.  migan_profile_step returns, for
+ * step `index` of the current plan, its label ("<state_dict prefix><kernel>"), the duration of
+ * its most recent launch (synchronizes on its end event), and its algorithmic bytes / flops
+ * (own inputs read once + output written once). */
+int migan_set_profiling(migan_ctx* ctx, int enable);
+int migan_profile_num_steps(const migan_ctx* ctx);
+int migan_profile_step(migan_ctx* ctx, int index, const char** label, float* ms, double* alg_bytes, double* flops);
+
 /* Debug/test tap: during the next forwards, copy the named intermediate (converted to NCHW
  * fp32) into `dst` (device pointer, large enough).  name == NULL clears the tap.  Names follow
  * the oracle's tap names (oracle/migan_oracle.py), e.g. "encoder.b256.conv1.out". */

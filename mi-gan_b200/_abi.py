@@ -27,6 +27,9 @@ SYMBOLS = [
     ("migan_host_staging_bytes", c_size_t, [c_void_p, c_int]),
     ("migan_forward_host", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     ("migan_last_launch_count", c_int, [c_void_p]),
+    ("migan_set_profiling", c_int, [c_void_p, c_int]),
+    ("migan_profile_num_steps", c_int, [c_void_p]),
+    ("migan_profile_step", c_int, [c_void_p, c_int, POINTER(c_char_p), POINTER(c_float), POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
     ("migan_set_tap", c_int, [c_void_p, c_char_p, c_void_p]),
     ("migan_tap_info", c_int, [c_void_p, c_int, c_int, POINTER(c_char_p), POINTER(c_int)]),
     ("b200_upfirdn2d", c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 14 + [c_int, c_float, c_void_p]),

@@ -103,6 +103,9 @@ struct Step {
     int act = 0;
     bool want_f32 = false;
     migan::SepconvTcArgs tc;  // resolved tcgen05 launch (tensor maps, tiling)
+    // roofline bookkeeping: algorithmic bytes = own input(s) read once + output written once
+    std::string label;
+    double alg_bytes = 0, flops = 0;
     // tap (debug): tensor produced by this step
     std::string tap;
     const float* tap_src = nullptr;
@@ -142,6 +145,8 @@ struct migan_ctx {
     int last_launches = 0;
     std::string tap_name;
     float* tap_dst = nullptr;
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;  // 2 per step of the current plan
 };
 
 namespace {
@@ -280,6 +285,7 @@ int migan_create(int resolution, int device, migan_ctx** out) {
 
 int migan_destroy(migan_ctx* ctx) {
     if (!ctx) return MIGAN_OK;
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->arena && ctx->device >= 0) {
         cudaSetDevice(ctx->device);
         cudaFree(ctx->arena);
@@ -610,7 +616,42 @@ struct PlanBuilder {
             steps.push_back(s);
             img_cur = img_next;
         }
+        annotate();
         return MIGAN_OK;
+    }
+
+    static const char* kernel_name(StepKind k) {
+        switch (k) {
+            case K_STEM: return "stem_fromrgb";
+            case K_DW: return "dw3x3_act";
+            case K_DWDOWN: return "dw3x3_down";
+            case K_GEMM_SIMT: return "pw_gemm_simt";
+            case K_SEPCONV_TC: return "sepconv_tc";
+            case K_UP2: return "up2_noise_act_skip";
+            case K_TORGB: return "torgb_img";
+            case K_ADD: return "add_inplace";
+        }
+        return "?";
+    }
+
+    void annotate() {
+        for (Step& s : steps) {
+            const double px = (double)s.n * s.H * s.W, f = sizeof(float);
+            switch (s.kind) {
+                case K_STEM: s.alg_bytes = px * (4 + s.C) * f; s.flops = px * s.C * 8; break;
+                case K_DW: s.alg_bytes = px * s.C * 2 * f; s.flops = px * s.C * 18; break;
+                case K_DWDOWN: s.alg_bytes = px * s.C * 1.25 * f; s.flops = px * s.C * (18 + 8); break;
+                case K_GEMM_SIMT: s.alg_bytes = px * (s.L->cin + s.L->cout) * f; s.flops = px * 2.0 * s.L->cin * s.L->cout; break;
+                case K_SEPCONV_TC:
+                    s.alg_bytes = px * (s.L->cin + s.L->cout) * f;
+                    s.flops = px * (2.0 * s.L->cin * s.L->cout + (s.in ? 18.0 * s.L->cin : 0.0));
+                    break;
+                case K_UP2: s.alg_bytes = px * s.C * f * (1 + 4 + (s.aux ? 4 : 0)); s.flops = px * 4 * s.C * 8; break;
+                case K_TORGB: s.alg_bytes = px * (s.C + 3 + (s.aux ? 0.75 : 0)) * f; s.flops = px * s.C * 6; break;
+                case K_ADD: s.alg_bytes = px * s.C * 3 * f; s.flops = px * s.C; break;
+            }
+            s.label = (s.L ? s.L->p : s.T ? s.T->p + "torgb." : std::string("encoder.fromrgb.")) + kernel_name(s.kind);
+        }
     }
 };
 
@@ -691,9 +732,44 @@ int migan_forward(migan_ctx* ctx, const float* x, float* y, int n, void* workspa
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ctx->last_launches = 0;
+    if (ctx->profiling) {
+        while (ctx->events.size() < 2 * ctx->plan.steps.size()) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreate(&e));
+            ctx->events.push_back(e);
+        }
+    }
+    size_t i = 0;
     for (const Step& s : ctx->plan.steps) {
+        if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->events[2 * i], st));
         int rc = run_step(ctx, s, x, y, st);
         if (rc) return rc;
+        if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->events[2 * i + 1], st));
+        ++i;
+    }
+    return MIGAN_OK;
+}
+
+int migan_set_profiling(migan_ctx* ctx, int enable) {
+    if (!ctx) return fail(MIGAN_ERR_INVALID, "null ctx");
+    ctx->profiling = enable != 0;
+    return MIGAN_OK;
+}
+
+int migan_profile_num_steps(const migan_ctx* ctx) { return ctx ? (int)ctx->plan.steps.size() : 0; }
+
+int migan_profile_step(migan_ctx* ctx, int index, const char** label, float* ms, double* alg_bytes, double* flops) {
+    if (!ctx || index < 0 || index >= (int)ctx->plan.steps.size()) return fail(MIGAN_ERR_INVALID, "bad step index %d", index);
+    const Step& s = ctx->plan.steps[index];
+    if (label) *label = s.label.c_str();
+    if (alg_bytes) *alg_bytes = s.alg_bytes;
+    if (flops) *flops = s.flops;
+    if (ms) {
+        *ms = 0.f;
+        if (ctx->events.size() >= 2 * (size_t)index + 2) {
+            CUDA_TRY(cudaEventSynchronize(ctx->events[2 * index + 1]));
+            CUDA_TRY(cudaEventElapsedTime(ms, ctx->events[2 * index], ctx->events[2 * index + 1]));
+        }
     }
     return MIGAN_OK;
 }

@@ -62,7 +62,7 @@ struct Params {
     int tile_n, tile_h, tile_w, n_tile;      // n_tile = N per CTA tile (64 or 128)
     int tiles_x, tiles_y, tiles_n, num_n_tiles, num_tiles;
     int num_kb;                               // cin / 64
-    int in_stages, a_stages, b_stages, b_resident;
+    int in_stages, a_stages, b_stages, b_resident, epi_bufs;
     uint32_t in_chunk_bytes;                  // tile_n*(tile_h+2)*(tile_w+2)*128
     uint32_t in_stage_stride;                 // rounded to 1024
     uint32_t off_in, off_a, off_b, off_epi;   // smem offsets from the 1024-aligned base
@@ -156,7 +156,13 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The loaded registers are tied to the wait as in/out operands so the compiler cannot hoist
+// their uses above it (tcgen05.ld is asynchronous until wait::ld).
+__device__ __forceinline__ void tc_wait_ld(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
 
 // UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, rows of 64 fp16 (128 B),
 // 8-row groups 1024 B apart (SBO).  Bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor.
@@ -279,7 +285,11 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
             const int acc = it & 1;
             mbar_wait(empty_acc(acc), ((it >> 1) & 1) ^ 1, 200 + acc, p.error_flag);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.n_tile);
+            // Accumulator stage = [main | correction] column blocks.  The 2^-11-sized correction products
+            // (Al*Bh + Ah*Bl) go to their own accumulator: the tensor core truncates on every accumulate,
+            // and adding them into the large main sum would cost ~0.5 ulp of the MAIN sum per MMA.
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 2 * p.n_tile);
+            const uint32_t tmem_c = tmem_d + (uint32_t)p.n_tile;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int kbc = it * num_kb + kb;
                 const int sa = kbc % p.a_stages;
@@ -297,8 +307,8 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 16 fp16 = 32 bytes along K inside the SW128 row
                         tc_mma_f16(tmem_d, dah + adv, dbh + adv, idesc, (kb | k) != 0);
                         if (p.passes == 3) {
-                            tc_mma_f16(tmem_d, dal + adv, dbh + adv, idesc, 1u);
-                            tc_mma_f16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+                            tc_mma_f16(tmem_c, dal + adv, dbh + adv, idesc, (kb | k) != 0);
+                            tc_mma_f16(tmem_c, dah + adv, dbl + adv, idesc, 1u);
                         }
                     }
                     tc_commit(empty_a(sa));                       // A slot reusable once these MMAs retire
@@ -326,8 +336,16 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
             if (p.noise) nz = __ldg(p.noise + (tc.y0 + yl) * p.W + tc.x0 + xl);
             for (int j = 0; j < chunks; ++j) {
                 uint32_t v[32];
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_tile + j * 32), v);
-                tc_wait_ld();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * p.n_tile + j * 32);
+                tc_ld32(taddr, v);
+                tc_wait_ld(v);
+                if (p.passes == 3) {
+                    uint32_t c[32];
+                    tc_ld32(taddr + (uint32_t)p.n_tile, c);
+                    tc_wait_ld(c);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(c[i]));
+                }
                 if (j == chunks - 1) {               // accumulator fully read: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
@@ -340,7 +358,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                     o[i] = p.act ? lrelu_agc(f) : f;
                 }
                 // staging buffer `buf` must have been drained by the TMA store issued two chunks ago
-                if (issuer) tma_wait_group_read<1>();
+                if (issuer) { if (p.epi_bufs == 2) tma_wait_group_read<1>(); else tma_wait_group_read<0>(); }
                 named_bar_sync(1, 128);
                 const uint32_t dst = smem_base + p.off_epi + buf * kEpiBuf + row * 128;
 #pragma unroll
@@ -355,7 +373,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                     tma_store_4d(&p.map_out, smem_base + p.off_epi + buf * kEpiBuf, tc.nt * p.n_tile + j * 32, tc.x0, tc.y0, tc.n0);
                     tma_commit_group();
                 }
-                buf ^= 1;
+                buf = (buf + 1 == p.epi_bufs) ? 0 : buf + 1;
             }
         }
         if (issuer) tma_wait_group_all();
@@ -516,15 +534,23 @@ const char* sepconv_tc_plan(SepconvTcArgs* args, int passes, const float* in_f32
     // ---- shared-memory budget -> stage counts ----
     const uint32_t b_stage = (uint32_t)p.n_tile * kKBlock * 2 * 2;
     const uint32_t budget = kSmemLimit - 4096 - 1024;   // static smem + alignment slack
-    const uint32_t epi = 2 * kEpiBuf;
+    // The input ring is shared by the two prologue groups (even chunks -> group 0, odd -> group 1):
+    // the stage count must be EVEN so that each stage always belongs to one group and every waiter
+    // observes every phase of its barriers (parity waits alias otherwise).
     p.b_resident = (p.num_n_tiles == 1 && (uint32_t)p.num_kb * b_stage <= 65536) ? 1 : 0;
     p.b_stages = p.b_resident ? p.num_kb : 2;
     p.a_stages = (p.a_mode == 0) ? 2 : 3;
+    p.epi_bufs = 2;
+    uint32_t epi = p.epi_bufs * kEpiBuf;
     uint32_t fixed = epi + p.a_stages * kAStage + p.b_stages * b_stage;
     if (p.a_mode == 0) {
+        if (fixed + 2 * p.in_stage_stride > budget) {   // small-resolution tiles carry a large halo: drop to one staging buffer
+            p.epi_bufs = 1;
+            epi = kEpiBuf;
+            fixed = epi + p.a_stages * kAStage + p.b_stages * b_stage;
+        }
         if (fixed + 2 * p.in_stage_stride > budget) return "shared memory budget exceeded";
-        p.in_stages = std::min<int>(kMaxStages, (budget - fixed) / p.in_stage_stride);
-        p.in_stages = std::min(p.in_stages, 6);
+        p.in_stages = std::min<int>(6, (budget - fixed) / p.in_stage_stride) & ~1;
     } else {
         p.in_stages = 0;
         if (fixed > budget) return "shared memory budget exceeded";

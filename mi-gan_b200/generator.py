@@ -221,6 +221,23 @@ class Generator(nn.Module):
         eng = next(iter(self._engines.values())) if device is None else self._engines[torch.device(device)]
         return int(eng.lib.migan_last_launch_count(eng.handle))
 
+    def set_profiling(self, enable: bool, device=None) -> None:
+        """Bracket every kernel launch of subsequent forwards with CUDA events (roofline reports)."""
+        eng = self._engine(next(self.parameters()).device if device is None else torch.device(device))
+        _abi.check(eng.lib.migan_set_profiling(eng.handle, int(bool(enable))))
+
+    def profile_steps(self, device=None):
+        """[(label, ms, algorithmic_bytes, flops)] of the most recent profiled forward."""
+        eng = self._engine(next(self.parameters()).device if device is None else torch.device(device))
+        out = []
+        label, ms = ctypes.c_char_p(), ctypes.c_float()
+        nbytes, flops = ctypes.c_double(), ctypes.c_double()
+        for i in range(eng.lib.migan_profile_num_steps(eng.handle)):
+            _abi.check(eng.lib.migan_profile_step(eng.handle, i, ctypes.byref(label), ctypes.byref(ms),
+                                                  ctypes.byref(nbytes), ctypes.byref(flops)))
+            out.append((label.value.decode(), float(ms.value), float(nbytes.value), float(flops.value)))
+        return out
+
     def tap_names(self, device=None):
         """[(name, (C, H, W))] of the intermediates `forward_with_tap` can return on the current path."""
         eng = self._engine(next(self.parameters()).device if device is None else torch.device(device))
