@@ -102,12 +102,50 @@ def measured_peaks():
         return HBM_FALLBACK_GBS, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
+def usable_cpus() -> int:
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:  # cgroup v2 CPU quota
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
+def pick_cpu_threads(res: int) -> int:
+    """All the host threads the CPU path can actually use: oneDNN stops scaling (and collapses when
+    the container's CPU quota is below the visible core count), so calibrate on a small case."""
+    from oracle import migan_oracle as O
+
+    limit = usable_cpus()
+    cands = sorted({c for c in (8, 16, 32, 64, limit) if c <= limit} | {min(limit, 8)})
+    r = min(res, 128)
+    sd = O.make_state_dict(r, seed=1)
+    x = O.make_input(r, 1, seed=1)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        O.generator_forward(sd, x, r)
+        t0 = time.perf_counter()
+        O.generator_forward(sd, x, r)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_reference_forward_rate(res: int, seconds: float, max_iters: int, warmup: int = 1):
     """The reference algorithm on the host cores: oracle port (same torch CPU ops as
     lib/model_zoo/migan_inference.py), batch 1 (fastest per image on CPU)."""
     from oracle import migan_oracle as O  # checker / CPU baseline only
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    threads = pick_cpu_threads(res)
     sd = O.make_state_dict(res, seed=1)
     x = O.make_input(res, 1, seed=1234)
     for _ in range(warmup):
@@ -118,7 +156,7 @@ def cpu_reference_forward_rate(res: int, seconds: float, max_iters: int, warmup:
         t0 = time.perf_counter()
         O.generator_forward(sd, x, res)
         times.append(time.perf_counter() - t0)
-    return len(times) / sum(times), len(times), torch.get_num_threads()
+    return len(times) / sum(times), len(times), threads
 
 
 # ------------------------------------------------------------------------------------------
@@ -130,7 +168,7 @@ def run_reference(args):
         return
     from oracle import migan_oracle as O
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    pick_cpu_threads(args.res)
     sd = O.make_state_dict(args.res, seed=1)
     x = O.make_input(args.res, 1, seed=1234)
     for _ in range(max(args.warmup, 1)):

@@ -9,6 +9,8 @@
 //   up2       : Upsample2d (zero insertion, pad (2,1,2,1), 4x4 FIR) + noise + activation,
 //               then the decoder skip add                                :98-103, :165-169, :304-305
 //   torgb     : SynthesisBlock torgb 1x1 + Upsample2d of the image + add :308-313
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -21,18 +23,22 @@ static inline unsigned blocks_for(int64_t items, int threads) {
 // --------------------------------------------------------------------------------------
 // stem: x NCHW [n,4,H,W] -> NHWC [n,H,W,C0]
 // --------------------------------------------------------------------------------------
+// All spatial sizes and channel counts are powers of two: index math is 32-bit shifts/masks
+// (64-bit div/mod costs ~100 instructions per thread and dominated these kernels otherwise).
+__device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
+
 __global__ void __launch_bounds__(256)
 stem_fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                    float* __restrict__ out, int64_t npix, int HW, int C0) {
-    const int cv = C0 >> 2;
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= npix * cv) return;
-    const int c4 = (int)(idx % cv);
-    const int64_t p = idx / cv;
-    const int64_t img = p / HW;
-    const int64_t q = p - img * HW;
-    const float* xp = x + img * 4 * (int64_t)HW + q;
-    const float x0 = __ldg(xp), x1 = __ldg(xp + HW), x2 = __ldg(xp + 2 * (int64_t)HW), x3 = __ldg(xp + 3 * (int64_t)HW);
+                    float* __restrict__ out, uint32_t items, int lhw, int lcv) {
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    if (idx >= items) return;
+    const uint32_t c4 = idx & ((1u << lcv) - 1);
+    const uint32_t p = idx >> lcv;
+    const uint32_t q = p & ((1u << lhw) - 1);
+    const uint32_t img = p >> lhw;
+    const size_t HW = (size_t)1 << lhw;
+    const float* xp = x + (size_t)img * 4 * HW + q;
+    const float x0 = __ldg(xp), x1 = __ldg(xp + HW), x2 = __ldg(xp + 2 * HW), x3 = __ldg(xp + 3 * HW);
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -44,15 +50,31 @@ stem_fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ w, co
         v = fmaf(wc.w, x3, v);
         o[j] = lrelu_agc(v + __ldg(b + c));
     }
-    stg4(out + p * C0 + c4 * 4, make_float4(o[0], o[1], o[2], o[3]));
+    stg4(out + ((size_t)p << (lcv + 2)) + c4 * 4, make_float4(o[0], o[1], o[2], o[3]));
 }
+
+// Launch helper: split the batch so that one launch indexes < 2^31 work items.
+template <typename F>
+static cudaError_t for_image_groups(int n, size_t items_per_image, F&& launch) {
+    const int max_imgs = (int)std::max<size_t>(1, ((size_t)1 << 31) / std::max<size_t>(items_per_image, 1));
+    for (int i0 = 0; i0 < n; i0 += max_imgs) {
+        launch(i0, std::min(max_imgs, n - i0));
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+static inline int host_log2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 cudaError_t launch_stem(const float* x, const float* w, const float* b, float* out,
                         int n, int H, int W, int C0, cudaStream_t s) {
-    const int64_t npix = (int64_t)n * H * W;
-    const int64_t items = npix * (C0 / 4);
-    stem_fromrgb_kernel<<<blocks_for(items, 256), 256, 0, s>>>(x, w, b, out, npix, H * W, C0);
-    return cudaGetLastError();
+    const size_t per_img = (size_t)H * W * (C0 / 4);
+    return for_image_groups(n, per_img, [&](int i0, int cnt) {
+        const uint32_t items = (uint32_t)(per_img * cnt);
+        stem_fromrgb_kernel<<<(items + 255) / 256, 256, 0, s>>>(x + (size_t)i0 * 4 * H * W, w, b, out + (size_t)i0 * H * W * C0,
+                                                               items, host_log2(H * W), host_log2(C0 / 4));
+    });
 }
 
 // --------------------------------------------------------------------------------------
@@ -61,14 +83,14 @@ cudaError_t launch_stem(const float* x, const float* w, const float* b, float* o
 // --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 dw3x3_act_kernel(const float* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ bias,
-                 float* __restrict__ out, int64_t npix, int H, int W, int C) {
-    const int cv = C >> 2;
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= npix * cv) return;
-    const int c = (int)(idx % cv) * 4;
-    const int64_t p = idx / cv;
-    const int x = (int)(p % W);
-    const int y = (int)((p / W) % H);
+                 float* __restrict__ out, uint32_t items, int lw, int lh, int lcv) {
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    if (idx >= items) return;
+    const int W = 1 << lw, H = 1 << lh, C = 4 << lcv;
+    const int c = (int)(idx & ((1u << lcv) - 1)) * 4;
+    const uint32_t p = idx >> lcv;
+    const int x = (int)(p & (W - 1));
+    const int y = (int)((p >> lw) & (H - 1));
     float4 acc = ldg4(bias + c);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -78,114 +100,105 @@ dw3x3_act_kernel(const float* __restrict__ in, const float* __restrict__ w9, con
         for (int kx = 0; kx < 3; ++kx) {
             const int xx = x + kx - 1;
             if (xx < 0 || xx >= W) continue;
-            const int64_t q = p + (int64_t)(ky - 1) * W + (kx - 1);
+            const size_t q = (size_t)((int64_t)p + (ky - 1) * W + (kx - 1));
             fma4(acc, ldg4(w9 + (ky * 3 + kx) * C + c), ldg4(in + q * C + c));
         }
     }
-    stg4(out + p * C + c, lrelu_agc4(acc));
+    stg4(out + (size_t)p * C + c, lrelu_agc4(acc));
 }
 
 cudaError_t launch_dw3x3(const float* in, const float* w9, const float* bias, float* out,
                          int n, int H, int W, int C, cudaStream_t s) {
-    const int64_t npix = (int64_t)n * H * W;
-    dw3x3_act_kernel<<<blocks_for(npix * (C / 4), 256), 256, 0, s>>>(in, w9, bias, out, npix, H, W, C);
-    return cudaGetLastError();
+    const size_t per_img = (size_t)H * W * (C / 4);
+    return for_image_groups(n, per_img, [&](int i0, int cnt) {
+        const uint32_t items = (uint32_t)(per_img * cnt);
+        const size_t off = (size_t)i0 * H * W * C;
+        dw3x3_act_kernel<<<(items + 255) / 256, 256, 0, s>>>(in + off, w9, bias, out + off, items, host_log2(W), host_log2(H), host_log2(C / 4));
+    });
 }
 
 // --------------------------------------------------------------------------------------
-// depthwise 3x3 + bias + act + FIR 4x4 / stride 2 / pad 1, smem-tiled.
-//   block = TH x TW low-res outputs x CC channels of one image
-//   s_in : (2TH+4) x (2TW+4) input pixels (zero outside the image = conv padding 1)
-//   s_dw : (2TH+2) x (2TW+2) activated depthwise outputs (zero outside the image = FIR padding 1;
-//          NOT act(bias): the FIR pads the activated tensor, migan_inference.py:62-70)
+// depthwise 3x3 + bias + act + FIR 4x4 / stride 2 / pad 1.  One thread = one low-res output
+// pixel x 4 channels: it evaluates the 4x4 activated depthwise outputs the FIR needs from a
+// 6x6 input window (L1-served 128-bit loads; no block-level staging or barriers, so many warps
+// stay in flight).  Depthwise outputs outside the image are ZERO (the FIR zero-pads the
+// ACTIVATED tensor, migan_inference.py:62-70), not act(bias).
 // --------------------------------------------------------------------------------------
-template <int TH, int TW, int CC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 3)
 dw3x3_down_kernel(const float* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ bias,
                   const float* __restrict__ fir16, float* __restrict__ out_f32,
-                  __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int C) {
-    constexpr int IH = 2 * TH + 4, IW = 2 * TW + 4, DH = 2 * TH + 2, DW = 2 * TW + 2, CV = CC / 4;
-    extern __shared__ float4 smem_f4[];
-    float4* s_in = smem_f4;
-    float4* s_dw = smem_f4 + IH * IW * CV;
-
-    const int H2 = H >> 1, W2 = W >> 1;
-    const int tiles_x = (W2 + TW - 1) / TW;
-    const int ox0 = (blockIdx.x % tiles_x) * TW;
-    const int oy0 = (blockIdx.x / tiles_x) * TH;
-    const int c0 = blockIdx.y * CC;
-    const int64_t img = blockIdx.z;
-    const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
-    const int tid = threadIdx.x;
-
-    for (int i = tid; i < IH * IW * CV; i += 256) {
-        const int cv = i % CV, pos = i / CV;
-        const int gy = iy0 + pos / IW, gx = ix0 + pos % IW;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-            v = ldg4(in + ((img * H + gy) * W + gx) * C + c0 + cv * 4);
-        s_in[i] = v;
-    }
-    __syncthreads();
-    for (int i = tid; i < DH * DW * CV; i += 256) {
-        const int cv = i % CV, pos = i / CV;
-        const int dy = pos / DW, dx = pos % DW;
-        const int gy = 2 * oy0 - 1 + dy, gx = 2 * ox0 - 1 + dx;
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            const int c = c0 + cv * 4;
-            float4 acc = ldg4(bias + c);
+                  __half* __restrict__ out_hi, __half* __restrict__ out_lo, uint32_t items, int lw2, int lh2, int lcv) {
+    const uint32_t idx = blockIdx.x * 128u + threadIdx.x;
+    if (idx >= items) return;
+    const int W2 = 1 << lw2, H2 = 1 << lh2, W = 2 * W2, H = 2 * H2, C = 4 << lcv;
+    const int c = (int)(idx & ((1u << lcv) - 1)) * 4;
+    const uint32_t p = idx >> lcv;                       // low-res pixel index over the image group
+    const int ox = (int)(p & (W2 - 1));
+    const int oy = (int)((p >> lw2) & (H2 - 1));
+    const size_t img = p >> (lw2 + lh2);
+    const float* src = in + img * (size_t)H * W * C + c;
+    float4 wv[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wv[t] = ldg4(w9 + t * C + c);
+    const float4 bv = ldg4(bias + c);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // input rows 2*oy-2 .. 2*oy+3, columns 2*ox-2 .. 2*ox+3; rolling 3-row window of 6 columns
+    float4 r[3][6];
+    const int ix0 = 2 * ox - 2, iy0 = 2 * oy - 2;
+    auto load_row = [&](int slot, int iy) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int ix = ix0 + j;
+            r[slot][j] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? ldg4(src + ((size_t)iy * W + ix) * C)
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    load_row(0, iy0);
+    load_row(1, iy0 + 1);
+#pragma unroll
+    for (int ty = 0; ty < 4; ++ty) {                     // depthwise output row 2*oy-1+ty
+        load_row((ty + 2) % 3, iy0 + ty + 2);
+        const int gy = 2 * oy - 1 + ty;
+        if (gy < 0 || gy >= H) continue;
+#pragma unroll
+        for (int tx = 0; tx < 4; ++tx) {                 // depthwise output column 2*ox-1+tx
+            const int gx = 2 * ox - 1 + tx;
+            if (gx < 0 || gx >= W) continue;
+            float4 d = bv;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx)
-                    fma4(acc, ldg4(w9 + (ky * 3 + kx) * C + c), s_in[((dy + ky) * IW + dx + kx) * CV + cv]);
-            r = lrelu_agc4(acc);
+                for (int kx = 0; kx < 3; ++kx) fma4(d, wv[ky * 3 + kx], r[(ty + ky) % 3][tx + kx]);
+            fma4(acc, ldg4(fir16 + (ty * 4 + tx) * C + c), lrelu_agc4(d));
         }
-        s_dw[i] = r;
     }
-    __syncthreads();
-    for (int i = tid; i < TH * TW * CV; i += 256) {
-        const int cv = i % CV, pos = i / CV;
-        const int oy = pos / TW, ox = pos % TW;
-        if (oy0 + oy >= H2 || ox0 + ox >= W2) continue;
-        const int c = c0 + cv * 4;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int ty = 0; ty < 4; ++ty)
-#pragma unroll
-            for (int tx = 0; tx < 4; ++tx)
-                fma4(acc, ldg4(fir16 + (ty * 4 + tx) * C + c), s_dw[((2 * oy + ty) * DW + 2 * ox + tx) * CV + cv]);
-        const int64_t o = ((img * H2 + oy0 + oy) * W2 + ox0 + ox) * C + c;
-        if (out_f32) stg4(out_f32 + o, acc);
-        if (out_hi) {
-            __half h[4], l[4];
-            split_f16(acc.x, kActSplitScale, h[0], l[0]);
-            split_f16(acc.y, kActSplitScale, h[1], l[1]);
-            split_f16(acc.z, kActSplitScale, h[2], l[2]);
-            split_f16(acc.w, kActSplitScale, h[3], l[3]);
-            *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(h);
-            *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(l);
-        }
+    const size_t o = (size_t)p * C + c;
+    if (out_f32) stg4(out_f32 + o, acc);
+    if (out_hi) {
+        __half h[4], l[4];
+        split_f16(acc.x, kActSplitScale, h[0], l[0]);
+        split_f16(acc.y, kActSplitScale, h[1], l[1]);
+        split_f16(acc.z, kActSplitScale, h[2], l[2]);
+        split_f16(acc.w, kActSplitScale, h[3], l[3]);
+        *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(h);
+        *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(l);
     }
 }
 
-cudaError_t configure_elementwise() {
-    constexpr int TH = 8, TW = 8, CC = 32;
-    constexpr size_t smem = ((2 * TH + 4) * (2 * TW + 4) + (2 * TH + 2) * (2 * TW + 2)) * CC * sizeof(float);
-    return cudaFuncSetAttribute(dw3x3_down_kernel<TH, TW, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
+cudaError_t configure_elementwise() { return cudaSuccess; }
 
 cudaError_t launch_dw3x3_down(const float* in, const float* w9, const float* bias, const float* fir16,
                               float* out_f32, __half* out_hi, __half* out_lo,
                               int n, int H, int W, int C, cudaStream_t s) {
-    constexpr int TH = 8, TW = 8, CC = 32;
-    constexpr size_t smem = ((2 * TH + 4) * (2 * TW + 4) + (2 * TH + 2) * (2 * TW + 2)) * CC * sizeof(float);
-    auto kern = dw3x3_down_kernel<TH, TW, CC>;
     const int H2 = H / 2, W2 = W / 2;
-    dim3 grid(((W2 + TW - 1) / TW) * ((H2 + TH - 1) / TH), C / CC, n);
-    kern<<<grid, 256, smem, s>>>(in, w9, bias, fir16, out_f32, out_hi, out_lo, H, W, C);
-    return cudaGetLastError();
+    const size_t per_img = (size_t)H2 * W2 * (C / 4);
+    return for_image_groups(n, per_img, [&](int i0, int cnt) {
+        const uint32_t items = (uint32_t)(per_img * cnt);
+        const size_t oi = (size_t)i0 * H * W * C, oo = (size_t)i0 * H2 * W2 * C;
+        dw3x3_down_kernel<<<(items + 127) / 128, 128, 0, s>>>(in + oi, w9, bias, fir16, out_f32 ? out_f32 + oo : nullptr,
+                                                             out_hi ? out_hi + oo : nullptr, out_lo ? out_lo + oo : nullptr,
+                                                             items, host_log2(W2), host_log2(H2), host_log2(C / 4));
+    });
 }
 
 // --------------------------------------------------------------------------------------
@@ -195,16 +208,16 @@ cudaError_t launch_dw3x3_down(const float* in, const float* w9, const float* bia
 __global__ void __launch_bounds__(256)
 up2_noise_act_skip_kernel(const float* __restrict__ t, const float* __restrict__ fir16,
                           const float* __restrict__ noise, const float* __restrict__ skip,
-                          float* __restrict__ out, int64_t npix_out, int h, int w, int C) {
-    const int cv = C >> 2;
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= npix_out * cv) return;
-    const int c = (int)(idx % cv) * 4;
-    const int64_t p = idx / cv;
-    const int W2 = 2 * w, H2 = 2 * h;
-    const int ox = (int)(p % W2);
-    const int oy = (int)((p / W2) % H2);
-    const int64_t img = p / ((int64_t)W2 * H2);
+                          float* __restrict__ out, uint32_t items, int lw, int lh, int lcv) {
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    if (idx >= items) return;
+    const int w = 1 << lw, h = 1 << lh, W2 = 2 * w, H2 = 2 * h, C = 4 << lcv;
+    const int c = (int)(idx & ((1u << lcv) - 1)) * 4;
+    const uint32_t p = idx >> lcv;
+    const int ox = (int)(p & (W2 - 1));
+    const int oy = (int)((p >> (lw + 1)) & (H2 - 1));
+    const size_t img = p >> (lw + lh + 2);
+    const float* src = t + img * (size_t)h * w * C + c;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
@@ -216,7 +229,7 @@ up2_noise_act_skip_kernel(const float* __restrict__ t, const float* __restrict__
             const int tx = (ox & 1) + 2 * bb;
             const int ix = (ox + tx - 2) >> 1;
             if (ix < 0 || ix >= w) continue;
-            fma4(acc, ldg4(fir16 + (ty * 4 + tx) * C + c), ldg4(t + ((img * h + iy) * w + ix) * C + c));
+            fma4(acc, ldg4(fir16 + (ty * 4 + tx) * C + c), ldg4(src + ((size_t)iy * w + ix) * C));
         }
     }
     if (noise) {
@@ -224,18 +237,23 @@ up2_noise_act_skip_kernel(const float* __restrict__ t, const float* __restrict__
         acc.x += nz; acc.y += nz; acc.z += nz; acc.w += nz;
     }
     acc = lrelu_agc4(acc);
+    const size_t o = (size_t)p * C + c;
     if (skip) {
-        const float4 sk = ldg4(skip + p * C + c);
+        const float4 sk = ldg4(skip + o);
         acc.x += sk.x; acc.y += sk.y; acc.z += sk.z; acc.w += sk.w;
     }
-    stg4(out + p * C + c, acc);
+    stg4(out + o, acc);
 }
 
 cudaError_t launch_up2(const float* t, const float* fir16, const float* noise, const float* skip,
                        float* out, int n, int h, int w, int C, cudaStream_t s) {
-    const int64_t npix = (int64_t)n * 4 * h * w;
-    up2_noise_act_skip_kernel<<<blocks_for(npix * (C / 4), 256), 256, 0, s>>>(t, fir16, noise, skip, out, npix, h, w, C);
-    return cudaGetLastError();
+    const size_t per_img = (size_t)4 * h * w * (C / 4);
+    return for_image_groups(n, per_img, [&](int i0, int cnt) {
+        const uint32_t items = (uint32_t)(per_img * cnt);
+        const size_t oi = (size_t)i0 * h * w * C, oo = (size_t)i0 * 4 * h * w * C;
+        up2_noise_act_skip_kernel<<<(items + 255) / 256, 256, 0, s>>>(t + oi, fir16, noise, skip ? skip + oo : nullptr, out + oo,
+                                                                     items, host_log2(w), host_log2(h), host_log2(C / 4));
+    });
 }
 
 // --------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -112,6 +113,10 @@ struct Step {
     int tapC = 0, tapH = 0, tapW = 0;
     bool tap_planar = false;
     int tap_flags = 0;
+    // second tap (fused torgb: the image produced by the same launch)
+    std::string tap2;
+    const float* tap2_src = nullptr;
+    int tap2C = 0, tap2H = 0, tap2W = 0, tap2_flags = 0;
 };
 
 struct Plan {
@@ -508,7 +513,8 @@ struct PlanBuilder {
     // Emit one SeparableConv2d reading `in` (NHWC [n,res_in,res_in,cin]); `skip` is added after the
     // final activation (decoder conv1, migan_inference.py:304-305).  Returns the output pointer.
     // in_idx: scratch index holding `in` (or -1 if it is a feat buffer); out_fixed: write there if non-null.
-    int emit_sepconv(const SepConv& L, const float* in, int in_idx, float* out_fixed, const float* skip, int& out_idx, float*& out_ptr) {
+    int emit_sepconv(const SepConv& L, const float* in, int in_idx, float* out_fixed, const float* skip, int& out_idx, float*& out_ptr,
+                     const migan::SepconvTcRgb* rgb = nullptr, const std::string& rgb_tap = std::string(), int rgb_flags = 0) {
         const int t1 = other(in_idx), t2 = other(in_idx, t1);
         const bool tc = (path != MIGAN_PATH_SIMT);
         const float* gemm_in = nullptr;
@@ -546,12 +552,16 @@ struct PlanBuilder {
                 s.in = L.down ? nullptr : in;  // down: A operand comes pre-split from K_DWDOWN
                 s.hi = ghi; s.lo = glo;
                 const char* err = migan::sepconv_tc_plan(&s.tc, path == MIGAN_PATH_TC_FAST ? 1 : 3, s.in, ghi, glo, L.w9, L.bias,
-                                                         L.pw_hi, L.pw_lo, L.tc_inv_scale, s.aux, pw_out, n, L.res_pw, L.cin, L.cout, s.act);
+                                                         L.pw_hi, L.pw_lo, L.tc_inv_scale, s.aux, pw_out, n, L.res_pw, L.cin, L.cout, s.act, rgb);
+                if (rgb) {
+                    s.io_flags |= rgb_flags;
+                    s.tap2 = rgb_tap; s.tap2_src = rgb->img_out; s.tap2C = 3; s.tap2H = L.res_pw; s.tap2W = L.res_pw; s.tap2_flags = rgb_flags;
+                }
                 if (err) return fail(MIGAN_ERR_CUDA, "tcgen05 plan for %s failed: %s", L.p.c_str(), err);
             } else {
                 s.kind = K_GEMM_SIMT; s.in = gemm_in;
             }
-            set_tap(s, L.p + (raw ? "pw" : "out"), pw_out, L.cout, L.res_pw, L.res_pw);
+            if (!(rgb && !rgb->store_out)) set_tap(s, L.p + (raw ? "pw" : "out"), pw_out, L.cout, L.res_pw, L.res_pw);
             steps.push_back(s);
         }
         out_ptr = pw_out; out_idx = pw_idx;
@@ -603,17 +613,29 @@ struct PlanBuilder {
             int rc = emit_sepconv(c->syn1[i], cur, cur_idx, nullptr, feat[r], oi, op);  // x = conv1(x) + enc_feat
             if (rc) return rc;
             cur = op; cur_idx = oi;
-            rc = emit_sepconv(c->syn2[i], cur, cur_idx, nullptr, nullptr, oi, op);
-            if (rc) return rc;
-            cur = op; cur_idx = oi;
             const bool last = (i + 1 == c->syn_res.size());
-            Step s; s.kind = K_TORGB; s.T = &c->torgb[i]; s.in = cur; s.n = n; s.H = r; s.W = r; s.C = channels(r);
-            s.aux = (img_cur >= 0) ? IMG[img_cur] : nullptr;
             const int img_next = (img_cur < 0) ? 0 : 1 - img_cur;
-            if (last) { s.io_flags = PTR_Y; s.out = nullptr; }
-            else s.out = IMG[img_next];
-            set_tap(s, c->torgb[i].p + "img", s.out, 3, r, r, true, last ? PTR_Y : 0);
-            steps.push_back(s);
+            const float* img_lo = (img_cur >= 0) ? IMG[img_cur] : nullptr;
+            float* img_out = last ? nullptr : IMG[img_next];      // last level: the caller's y (bound at launch)
+            const ToRgb& T = c->torgb[i];
+            const bool fuse = (path != MIGAN_PATH_SIMT) && channels(r) <= 128;
+            if (fuse) {
+                migan::SepconvTcRgb rgb;
+                rgb.w = T.w; rgb.b = T.b; rgb.fir = T.fir; rgb.img_lo = img_lo; rgb.img_out = img_out; rgb.store_out = last ? 0 : 1;
+                rc = emit_sepconv(c->syn2[i], cur, cur_idx, nullptr, nullptr, oi, op, &rgb, T.p + "img", last ? PTR_Y : 0);
+                if (rc) return rc;
+                cur = op; cur_idx = oi;
+            } else {
+                rc = emit_sepconv(c->syn2[i], cur, cur_idx, nullptr, nullptr, oi, op);
+                if (rc) return rc;
+                cur = op; cur_idx = oi;
+                Step s; s.kind = K_TORGB; s.T = &T; s.in = cur; s.n = n; s.H = r; s.W = r; s.C = channels(r);
+                s.aux = img_lo;
+                if (last) { s.io_flags = PTR_Y; s.out = nullptr; }
+                else s.out = img_out;
+                set_tap(s, T.p + "img", s.out, 3, r, r, true, last ? PTR_Y : 0);
+                steps.push_back(s);
+            }
             img_cur = img_next;
         }
         annotate();
@@ -645,6 +667,11 @@ struct PlanBuilder {
                 case K_SEPCONV_TC:
                     s.alg_bytes = px * (s.L->cin + s.L->cout) * f;
                     s.flops = px * (2.0 * s.L->cin * s.L->cout + (s.in ? 18.0 * s.L->cin : 0.0));
+                    if (!s.tap2.empty()) {   // fused torgb: + image in/out, - feature map if it is not stored
+                        s.alg_bytes += px * 3.75 * f;
+                        s.flops += px * s.L->cout * 6;
+                        if (s.tap.empty()) s.alg_bytes -= px * s.L->cout * f;
+                    }
                     break;
                 case K_UP2: s.alg_bytes = px * s.C * f * (1 + 4 + (s.aux ? 4 : 0)); s.flops = px * 4 * s.C * 8; break;
                 case K_TORGB: s.alg_bytes = px * (s.C + 3 + (s.aux ? 0.75 : 0)) * f; s.flops = px * s.C * 6; break;
@@ -684,7 +711,7 @@ int run_step(migan_ctx* ctx, const Step& s, const float* x, float* y, cudaStream
                                            s.aux, s.H * s.W, s.act, st);
             break;
         case K_SEPCONV_TC:
-            e = migan::launch_sepconv_tc(s.tc, st);
+            e = migan::launch_sepconv_tc(s.tc, st, (s.io_flags & PTR_Y) ? y : nullptr);
             break;
         case K_UP2:
             e = migan::launch_up2(in, s.L->fir16, s.L->noise ? s.L->noise_dev : nullptr, s.aux, out, s.n, s.H, s.W, s.C, st);
@@ -705,6 +732,11 @@ int run_step(migan_ctx* ctx, const Step& s, const float* x, float* y, cudaStream
             e = cudaMemcpyAsync(ctx->tap_dst, src, sizeof(float) * (size_t)s.n * s.tapC * s.tapH * s.tapW, cudaMemcpyDeviceToDevice, st);
         else
             e = migan::launch_nhwc_to_nchw(src, ctx->tap_dst, s.n, s.tapH, s.tapW, s.tapC, st);
+        if (e != cudaSuccess) return fail(MIGAN_ERR_CUDA, "tap copy failed: %s", cudaGetErrorString(e));
+    }
+    if (ctx->tap_dst && !s.tap2.empty() && s.tap2 == ctx->tap_name) {
+        const float* src = (s.tap2_flags & PTR_Y) ? y : s.tap2_src;
+        e = cudaMemcpyAsync(ctx->tap_dst, src, sizeof(float) * (size_t)s.n * s.tap2C * s.tap2H * s.tap2W, cudaMemcpyDeviceToDevice, st);
         if (e != cudaSuccess) return fail(MIGAN_ERR_CUDA, "tap copy failed: %s", cudaGetErrorString(e));
     }
     return MIGAN_OK;
@@ -809,31 +841,27 @@ int migan_tap_info(const migan_ctx* ctx, int path, int index, const char** name,
     if (!ctx) return fail(MIGAN_ERR_INVALID, "null ctx");
     // Build a throw-away plan for n = 1 on a fake base (no kernels are launched; tc plans need
     // finalized weights only for pointers, which are not dereferenced here).
-    static thread_local std::vector<Step> cache;
+    static thread_local std::vector<std::pair<std::string, std::array<int, 3>>> cache;
     static thread_local const migan_ctx* cache_ctx = nullptr;
     static thread_local int cache_path = -1;
     if (cache_ctx != ctx || cache_path != path) {
+        // Build a throw-away plan for n = 1 on a fake base address (nothing is launched; tensor maps are
+        // only encoded, never dereferenced).
         PlanBuilder pb;
-        // Enumerate with the CUDA-core builder (no tensor maps needed); the tensor-core paths fuse
-        // the depthwise / FIR-down stages away, so their taps are filtered out below.
-        pb.c = const_cast<migan_ctx*>(ctx); pb.n = 1; pb.path = MIGAN_PATH_SIMT;
-        pb.base = reinterpret_cast<unsigned char*>(uintptr_t(1) << 20);
-        if (pb.build()) return MIGAN_ERR_INVALID;
+        pb.c = const_cast<migan_ctx*>(ctx); pb.n = 1; pb.path = path;
+        pb.base = reinterpret_cast<unsigned char*>(uintptr_t(1) << 30);
+        int rc = pb.build();
+        if (rc) return rc;
         cache.clear();
         for (Step& s : pb.steps) {
-            if (s.tap.empty()) continue;
-            if (path != MIGAN_PATH_SIMT) {
-                const std::string& t = s.tap;
-                auto ends = [&](const char* suf) { size_t l = strlen(suf); return t.size() >= l && t.compare(t.size() - l, l, suf) == 0; };
-                if (ends(".dw_act") || ends(".down")) continue;
-            }
-            cache.push_back(s);
+            if (!s.tap.empty()) cache.push_back({s.tap, {s.tapC, s.tapH, s.tapW}});
+            if (!s.tap2.empty()) cache.push_back({s.tap2, {s.tap2C, s.tap2H, s.tap2W}});
         }
         cache_ctx = ctx; cache_path = path;
     }
     if (index < 0 || index >= (int)cache.size()) return MIGAN_ERR_INVALID;
-    if (name) *name = cache[index].tap.c_str();
-    if (shape) { shape[0] = cache[index].tapC; shape[1] = cache[index].tapH; shape[2] = cache[index].tapW; }
+    if (name) *name = cache[index].first.c_str();
+    if (shape) { shape[0] = cache[index].second[0]; shape[1] = cache[index].second[1]; shape[2] = cache[index].second[2]; }
     return MIGAN_OK;
 }
 

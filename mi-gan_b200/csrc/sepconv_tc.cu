@@ -66,6 +66,14 @@ struct Params {
     uint32_t in_chunk_bytes;                  // tile_n*(tile_h+2)*(tile_w+2)*128
     uint32_t in_stage_stride;                 // rounded to 1024
     uint32_t off_in, off_a, off_b, off_epi;   // smem offsets from the 1024-aligned base
+    int prefetch;                             // L2 prefetch distance of the producer, in chunks / K-blocks
+    // fused torgb + image path (SynthesisBlock.forward, migan_inference.py:308-313); needs num_n_tiles == 1
+    int torgb, store_out;
+    const float* rgb_w;                       // [3][cout]
+    const float* rgb_b;                       // [3]
+    const float* rgb_fir;                     // [16][3] up-sampling taps of the image path
+    const float* img_lo;                      // [n][3][H/2][W/2] planar, or null (first block)
+    float* img_out;                           // [n][3][H][W] planar
     int* error_flag;
 };
 
@@ -115,6 +123,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -202,6 +218,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
     //            [24,32) full_b  [32,40) empty_b  [40,42) full_acc  [42,44) empty_acc
     __shared__ __align__(8) uint64_t bars[44];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float s_rgb[3 * 128 + 4 + 48];   // torgb weights [3][cout<=128], bias[3(+1)], fir[16][3]
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -229,6 +246,11 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
         if (a_dw) prefetch_tensormap(&p.map_in); else { prefetch_tensormap(&p.map_a_hi); prefetch_tensormap(&p.map_a_lo); }
         prefetch_tensormap(&p.map_w_hi); prefetch_tensormap(&p.map_w_lo); prefetch_tensormap(&p.map_out);
     }
+    if (p.torgb) {
+        for (int i = threadIdx.x; i < 3 * p.cout; i += kThreads) s_rgb[i] = __ldg(p.rgb_w + i);
+        if (threadIdx.x < 3) s_rgb[3 * 128 + threadIdx.x] = __ldg(p.rgb_b + threadIdx.x);
+        if (threadIdx.x < 48 && p.img_lo) s_rgb[3 * 128 + 4 + threadIdx.x] = __ldg(p.rgb_fir + threadIdx.x);
+    }
     if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM by construction)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -245,6 +267,23 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             const uint32_t b_stage_bytes = (uint32_t)p.n_tile * kKBlock * 2 * 2;   // hi + lo
+            // L2 prefetch cursor: the smem rings are too shallow to cover HBM latency at full bandwidth
+            // (one 23 KB chunk per prologue group in flight), so the producer also asks the L2 for the
+            // data `prefetch` loads ahead (possibly in the next tile); the ring loads then hit L2.
+            const int total_loads = my_tiles * num_kb * (a_dw ? 2 : 1);
+            auto prefetch_load = [&](int c) {
+                if (c >= total_loads) return;
+                if (a_dw) {
+                    const int kbc = c >> 1, g = c & 1;
+                    const TileCoord t2 = decode_tile(p, blockIdx.x + (kbc / num_kb) * gridDim.x);
+                    tma_prefetch_4d(&p.map_in, (kbc % num_kb) * kKBlock + g * kChunkC, t2.x0 - 1, t2.y0 - 1, t2.n0);
+                } else {
+                    const int row0 = (blockIdx.x + (c / num_kb) * gridDim.x) / p.num_n_tiles * kTileM;
+                    tma_prefetch_2d(&p.map_a_hi, (c % num_kb) * kKBlock, row0);
+                    tma_prefetch_2d(&p.map_a_lo, (c % num_kb) * kKBlock, row0);
+                }
+            };
+            for (int c = 0; c < p.prefetch; ++c) prefetch_load(c);
             for (int it = 0; it < my_tiles; ++it) {
                 const TileCoord tc = decode_tile(p, blockIdx.x + it * gridDim.x);
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -253,6 +292,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                         for (int g = 0; g < 2; ++g) {
                             const int cc = 2 * kbc + g;
                             const int s = cc % p.in_stages;
+                            if (p.prefetch) prefetch_load(cc + p.prefetch);
                             mbar_wait(empty_in(s), ((cc / p.in_stages) & 1) ^ 1, 100 + s, p.error_flag);
                             mbar_expect_tx(full_in(s), p.in_chunk_bytes);
                             tma_load_4d(smem_base + p.off_in + s * p.in_stage_stride, &p.map_in, full_in(s),
@@ -260,6 +300,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                         }
                     } else {
                         const int s = kbc % p.a_stages;
+                        if (p.prefetch) prefetch_load(kbc + p.prefetch);
                         mbar_wait(empty_a(s), ((kbc / p.a_stages) & 1) ^ 1, 110 + s, p.error_flag);
                         mbar_expect_tx(full_a(s), kAStage);
                         const int row0 = (blockIdx.x + it * gridDim.x) / p.num_n_tiles * kTileM;
@@ -334,6 +375,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
             tc_fence_after();
             float nz = 0.f;
             if (p.noise) nz = __ldg(p.noise + (tc.y0 + yl) * p.W + tc.x0 + xl);
+            float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
             for (int j = 0; j < chunks; ++j) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * p.n_tile + j * 32);
@@ -357,6 +399,19 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                     float f = __uint_as_float(v[i]) * p.inv_scale + nz;
                     o[i] = p.act ? lrelu_agc(f) : f;
                 }
+                if (p.torgb) {                       // 1x1 conv Cout -> 3 on the activated row (weights broadcast from smem)
+                    const float4* w0 = reinterpret_cast<const float4*>(s_rgb + j * 32);
+                    const float4* w1 = reinterpret_cast<const float4*>(s_rgb + p.cout + j * 32);
+                    const float4* w2 = reinterpret_cast<const float4*>(s_rgb + 2 * p.cout + j * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 a = w0[i], b = w1[i], c = w2[i];
+                        rgb0 = fmaf(o[4 * i], a.x, rgb0); rgb0 = fmaf(o[4 * i + 1], a.y, rgb0); rgb0 = fmaf(o[4 * i + 2], a.z, rgb0); rgb0 = fmaf(o[4 * i + 3], a.w, rgb0);
+                        rgb1 = fmaf(o[4 * i], b.x, rgb1); rgb1 = fmaf(o[4 * i + 1], b.y, rgb1); rgb1 = fmaf(o[4 * i + 2], b.z, rgb1); rgb1 = fmaf(o[4 * i + 3], b.w, rgb1);
+                        rgb2 = fmaf(o[4 * i], c.x, rgb2); rgb2 = fmaf(o[4 * i + 1], c.y, rgb2); rgb2 = fmaf(o[4 * i + 2], c.z, rgb2); rgb2 = fmaf(o[4 * i + 3], c.w, rgb2);
+                    }
+                }
+                if (!p.store_out) continue;          // last block: the feature map is consumed by torgb only
                 // staging buffer `buf` must have been drained by the TMA store issued two chunks ago
                 if (issuer) { if (p.epi_bufs == 2) tma_wait_group_read<1>(); else tma_wait_group_read<0>(); }
                 named_bar_sync(1, 128);
@@ -375,9 +430,39 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                 }
                 buf = (buf + 1 == p.epi_bufs) ? 0 : buf + 1;
             }
+            if (p.torgb) {
+                // img = upsample(img_lo) + (torgb(x) + b)   (migan_inference.py:308-313); planar NCHW
+                const int img = tc.n0 + img_l, oy = tc.y0 + yl, ox = tc.x0 + xl;
+                if (img < p.n) {
+                    float r[3] = {rgb0 + s_rgb[384], rgb1 + s_rgb[385], rgb2 + s_rgb[386]};
+                    if (p.img_lo) {
+                        const int h = p.H >> 1, w = p.W >> 1;
+                        float up[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int a = 0; a < 2; ++a) {
+                            const int ty = (oy & 1) + 2 * a;
+                            const int iy = (oy + ty - 2) >> 1;
+                            if (iy < 0 || iy >= h) continue;
+#pragma unroll
+                            for (int bb = 0; bb < 2; ++bb) {
+                                const int tx = (ox & 1) + 2 * bb;
+                                const int ix = (ox + tx - 2) >> 1;
+                                if (ix < 0 || ix >= w) continue;
+#pragma unroll
+                                for (int k = 0; k < 3; ++k)
+                                    up[k] = fmaf(s_rgb[388 + (ty * 4 + tx) * 3 + k],
+                                                 __ldg(p.img_lo + (((size_t)img * 3 + k) * h + iy) * w + ix), up[k]);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) r[k] = up[k] + r[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) p.img_out[(((size_t)img * 3 + k) * p.H + oy) * p.W + ox] = r[k];
+                }
+            }
         }
         if (issuer) tma_wait_group_all();
-        (void)img_l;
     } else if (a_dw) {
         // ================================ prologue (depthwise) ========================
         const int g = (warp - kProWarp0) >> 2;            // channel half of the K-block this group produces
@@ -506,7 +591,8 @@ cudaError_t configure_sepconv_tc() {
 
 const char* sepconv_tc_plan(SepconvTcArgs* args, int passes, const float* in_f32, const __half* a_hi, const __half* a_lo,
                             const float* w9, const float* bias, const __half* w_hi, const __half* w_lo,
-                            float inv_scale, const float* noise, float* out, int n, int res, int cin, int cout, int act) {
+                            float inv_scale, const float* noise, float* out, int n, int res, int cin, int cout, int act,
+                            const SepconvTcRgb* rgb) {
     Params p;
     memset(&p, 0, sizeof(p));
     if (cin % kKBlock != 0 || cout % 64 != 0) return "cin must be a multiple of 64 and cout of 64";
@@ -562,6 +648,13 @@ const char* sepconv_tc_plan(SepconvTcArgs* args, int passes, const float* in_f32
     const uint32_t smem_bytes = p.off_epi + epi + 1024;
     if (smem_bytes > kSmemLimit - 4096) return "shared memory budget exceeded (layout)";
     p.error_flag = g_error_flag;
+    p.prefetch = (p.a_mode == 0) ? 4 : 2;
+    p.store_out = 1;
+    if (rgb) {
+        if (p.num_n_tiles != 1 || cout > 128) return "fused torgb needs all output channels in one CTA tile (cout <= 128)";
+        p.torgb = 1; p.store_out = rgb->store_out;
+        p.rgb_w = rgb->w; p.rgb_b = rgb->b; p.rgb_fir = rgb->fir; p.img_lo = rgb->img_lo; p.img_out = rgb->img_out;
+    }
 
     // ---- tensor maps ----
     const char* err = nullptr;
@@ -601,9 +694,10 @@ const char* sepconv_tc_plan(SepconvTcArgs* args, int passes, const float* in_f32
     return nullptr;
 }
 
-cudaError_t launch_sepconv_tc(const SepconvTcArgs& a, cudaStream_t s) {
+cudaError_t launch_sepconv_tc(const SepconvTcArgs& a, cudaStream_t s, float* img_out_override) {
     Params p;
     memcpy(&p, a.params_blob, sizeof(p));
+    if (img_out_override) p.img_out = img_out_override;
     sepconv_tc_kernel<<<a.grid, kThreads, a.smem_bytes, s>>>(p);
     return cudaGetLastError();
 }

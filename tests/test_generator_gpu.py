@@ -46,10 +46,11 @@ def test_forward_matches_oracle(cuda_device, path, R, N):
     assert mx < TOL_MAX_ABS and mean < TOL_MEAN_ABS
 
 
-@pytest.mark.parametrize("path", PATHS)
-def test_every_intermediate_matches_oracle(cuda_device, path):
-    """Walk the plan stage by stage (debug taps) so a failure names the first bad kernel."""
-    R, N = 64, 2
+@pytest.mark.parametrize("path,R", [("simt", 64), ("tc", 64), ("tc", 256)])
+def test_every_intermediate_matches_oracle(cuda_device, path, R):
+    """Walk the plan stage by stage (debug taps) so a failure names the first bad kernel.
+    R=256 on the tensor-core path also covers the fused torgb epilogue (C <= 128 levels)."""
+    N = 2
     g, sd = make_model(R, path)
     x = O.make_input(R, N, seed=5)
     taps = {}
