@@ -69,6 +69,8 @@ struct SepConv {
     // device pointers into the weight arena
     float* w9 = nullptr;      // [9][cin]   depthwise taps, tap-major
     float* bias = nullptr;    // [cin]
+    float* w9_tc = nullptr;   // same, pre-multiplied by kActSplitScale * sqrt(2) for the tcgen05 prologue
+    float* bias_tc = nullptr;
     float* pw_t = nullptr;    // [cin][cout] fp32 (CUDA-core GEMM)
     __half* pw_hi = nullptr;  // [cout][cin] fp16 hi part of w * 2^k   (tcgen05, K-major)
     __half* pw_lo = nullptr;  // [cout][cin] fp16 lo part
@@ -152,6 +154,8 @@ struct migan_ctx {
     float* tap_dst = nullptr;
     bool profiling = false;
     std::vector<cudaEvent_t> events;  // 2 per step of the current plan
+    int tap_cache_path = -1;          // tap enumeration cache (migan_tap_info)
+    std::vector<std::pair<std::string, std::array<int, 3>>> tap_cache;
 };
 
 namespace {
@@ -339,6 +343,20 @@ static int pack_sepconv(migan_ctx* ctx, SepConv& L, ArenaBuilder& ab, std::vecto
         size_t off = ab.alloc(sizeof(float) * cin);
         memcpy(ab.bytes.data() + off, b.data(), sizeof(float) * cin);
         fix.push_back({reinterpret_cast<void**>(&L.bias), off});
+    }
+    {   // tcgen05 prologue: activation gain and fp16-split scale folded into the depthwise taps
+        const float S = 64.0f /* kActSplitScale */ * 1.41421356237309515f;
+        const std::vector<float>& w = W(ctx, L.p + "conv1.weight");
+        const std::vector<float>& b = W(ctx, L.p + "conv1.bias");
+        size_t off = ab.alloc(sizeof(float) * 9 * cin);
+        float* d = reinterpret_cast<float*>(ab.bytes.data() + off);
+        for (int c = 0; c < cin; ++c)
+            for (int t = 0; t < 9; ++t) d[t * cin + c] = w[c * 9 + t] * S;
+        fix.push_back({reinterpret_cast<void**>(&L.w9_tc), off});
+        size_t offb = ab.alloc(sizeof(float) * cin);
+        float* db = reinterpret_cast<float*>(ab.bytes.data() + offb);
+        for (int c = 0; c < cin; ++c) db[c] = b[c] * S;
+        fix.push_back({reinterpret_cast<void**>(&L.bias_tc), offb});
     }
     {   // pointwise [cout,cin,1,1] -> fp32 [cin][cout] and fp16 hi/lo [cout][cin]
         const std::vector<float>& w = W(ctx, L.p + "conv2.weight");
@@ -551,7 +569,7 @@ struct PlanBuilder {
                 s.kind = K_SEPCONV_TC;
                 s.in = L.down ? nullptr : in;  // down: A operand comes pre-split from K_DWDOWN
                 s.hi = ghi; s.lo = glo;
-                const char* err = migan::sepconv_tc_plan(&s.tc, path == MIGAN_PATH_TC_FAST ? 1 : 3, s.in, ghi, glo, L.w9, L.bias,
+                const char* err = migan::sepconv_tc_plan(&s.tc, path == MIGAN_PATH_TC_FAST ? 1 : 3, s.in, ghi, glo, L.w9_tc, L.bias_tc,
                                                          L.pw_hi, L.pw_lo, L.tc_inv_scale, s.aux, pw_out, n, L.res_pw, L.cin, L.cout, s.act, rgb);
                 if (rgb) {
                     s.io_flags |= rgb_flags;
@@ -841,10 +859,9 @@ int migan_tap_info(const migan_ctx* ctx, int path, int index, const char** name,
     if (!ctx) return fail(MIGAN_ERR_INVALID, "null ctx");
     // Build a throw-away plan for n = 1 on a fake base (no kernels are launched; tc plans need
     // finalized weights only for pointers, which are not dereferenced here).
-    static thread_local std::vector<std::pair<std::string, std::array<int, 3>>> cache;
-    static thread_local const migan_ctx* cache_ctx = nullptr;
-    static thread_local int cache_path = -1;
-    if (cache_ctx != ctx || cache_path != path) {
+    migan_ctx* mctx = const_cast<migan_ctx*>(ctx);
+    auto& cache = mctx->tap_cache;
+    if (mctx->tap_cache_path != path) {
         // Build a throw-away plan for n = 1 on a fake base address (nothing is launched; tensor maps are
         // only encoded, never dereferenced).
         PlanBuilder pb;
@@ -857,7 +874,7 @@ int migan_tap_info(const migan_ctx* ctx, int path, int index, const char** name,
             if (!s.tap.empty()) cache.push_back({s.tap, {s.tapC, s.tapH, s.tapW}});
             if (!s.tap2.empty()) cache.push_back({s.tap2, {s.tap2C, s.tap2H, s.tap2W}});
         }
-        cache_ctx = ctx; cache_path = path;
+        mctx->tap_cache_path = path;
     }
     if (index < 0 || index >= (int)cache.size()) return MIGAN_ERR_INVALID;
     if (name) *name = cache[index].first.c_str();

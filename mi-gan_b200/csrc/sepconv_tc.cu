@@ -53,8 +53,8 @@ constexpr uint32_t kSmemLimit = 232448;              // 227 KB
 
 struct Params {
     CUtensorMap map_in, map_a_hi, map_a_lo, map_w_hi, map_w_lo, map_out;
-    const float* w9;
-    const float* bias;
+    const float* w9;                          // [9][cin] depthwise taps * (kActSplitScale * sqrt 2)
+    const float* bias;                        // [cin]              * (kActSplitScale * sqrt 2)
     const float* noise;
     float inv_scale;
     int n, H, W, cin, cout;
@@ -93,11 +93,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+    // suspend-time hint: let the hardware park the warp instead of burning issue slots on polling
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug must never hang the GPU -- report and trap instead.
@@ -108,9 +109,9 @@ __device__ __noinline__ void mbar_timeout(int code, uint32_t parity, int* error_
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code, int* error_flag) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) mbar_timeout(code, parity, error_flag);
+        if (++spins > (1u << 24)) mbar_timeout(code, parity, error_flag);
     }
 }
 
@@ -194,6 +195,70 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // Instruction descriptor (InstrDescriptor in the same header): D=f32, A=B=f16, K-major both, M=128.
 __device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+// fp32 s (|s| <= 16384) -> fp16 pair with hi + lo ~= s to 22 bits.  hi = s with the low 13 mantissa
+// bits cleared (exactly representable in fp16), lo = fp16(s - hi): no conversion back to fp32.
+__device__ __forceinline__ void split_pack4(const float4 s, uint2& hi, uint2& lo) {
+    const float hx = __uint_as_float(__float_as_uint(s.x) & 0xFFFFE000u), hy = __uint_as_float(__float_as_uint(s.y) & 0xFFFFE000u);
+    const float hz = __uint_as_float(__float_as_uint(s.z) & 0xFFFFE000u), hw = __uint_as_float(__float_as_uint(s.w) & 0xFFFFE000u);
+    __half2 a = __floats2half2_rn(hx, hy), b = __floats2half2_rn(hz, hw);
+    __half2 c = __floats2half2_rn(s.x - hx, s.y - hy), d = __floats2half2_rn(s.z - hz, s.w - hw);
+    hi.x = *reinterpret_cast<uint32_t*>(&a); hi.y = *reinterpret_cast<uint32_t*>(&b);
+    lo.x = *reinterpret_cast<uint32_t*>(&c); lo.y = *reinterpret_cast<uint32_t*>(&d);
+}
+
+// scaled activation: the depthwise weights/bias carry S = kActSplitScale * sqrt(2), so
+//   S * clamp(lrelu(v) * sqrt2, +-256) == clamp(max(v', 0.2 v'), +-256 * kActSplitScale),  v' = S v
+__device__ __forceinline__ float act_scaled(float v) {
+    v = fmaxf(v, v * kLreluAlpha);
+    return fminf(fmaxf(v, -kActClamp * kActSplitScale), kActClamp * kActSplitScale);
+}
+
+// One 32-channel input chunk -> its half of the A operand K-block (fp16 hi/lo, UMMA K-major SW128).
+// Thread = (column, 4-channel vector); it slides a 3x3 window down the TH rows of the tile: 3 LDS.128
+// per output row, all offsets compile-time (tile shape is a template parameter).
+template <int TN, int TH, int TW>
+__device__ __forceinline__ void prologue_chunk(const float4* __restrict__ sin, uint8_t* __restrict__ a_hi, uint8_t* __restrict__ a_lo,
+                                               const float* __restrict__ w9, const float* __restrict__ bias, int cin, int cg0,
+                                               int g, int tg) {
+    constexpr int NCOLS = TN * TW;
+    constexpr int ROW_F4 = (TW + 2) * 8;                   // float4 per halo'd input row (8 float4 / pixel)
+#pragma unroll
+    for (int rep = 0; rep < (NCOLS * 8 + 127) / 128; ++rep) {
+        const int item = tg + rep * 128;
+        const int cvec = item & 7, colidx = item >> 3;
+        const int col = (colidx & 3) * (NCOLS >> 2) + (colidx >> 2);   // spreads a warp over 4 distinct swizzle rows
+        const int img_l = col / TW, x = col % TW;
+        const int cg = cg0 + cvec * 4;
+        float4 w[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w[t] = ldg4(w9 + t * cin + cg);
+        const float4 bv = ldg4(bias + cg);
+        const float4* base = sin + (img_l * (TH + 2) * (TW + 2) + x) * 8 + cvec;
+        float4 r0[3], r1[3], r2[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { r0[d] = base[d * 8]; r1[d] = base[ROW_F4 + d * 8]; }
+        const uint32_t jchunk = (uint32_t)(g * 4 + (cvec >> 1));
+        const uint32_t sub = (uint32_t)(cvec & 1) * 8;
+#pragma unroll
+        for (int y = 0; y < TH; ++y) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) r2[d] = base[(y + 2) * ROW_F4 + d * 8];
+            float4 a = bv;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { fma4(a, w[d], r0[d]); fma4(a, w[3 + d], r1[d]); fma4(a, w[6 + d], r2[d]); }
+            a.x = act_scaled(a.x); a.y = act_scaled(a.y); a.z = act_scaled(a.z); a.w = act_scaled(a.w);
+            uint2 hi, lo;
+            split_pack4(a, hi, lo);
+            const int m = (img_l * TH + y) * TW + x;       // row of the M tile
+            const uint32_t off = (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u + ((jchunk ^ (uint32_t)(m & 7)) << 4) + sub;
+            *reinterpret_cast<uint2*>(a_hi + off) = hi;
+            *reinterpret_cast<uint2*>(a_lo + off) = lo;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { r0[d] = r1[d]; r1[d] = r2[d]; }
+        }
+    }
 }
 
 struct TileCoord {
@@ -375,6 +440,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
             tc_fence_after();
             float nz = 0.f;
             if (p.noise) nz = __ldg(p.noise + (tc.y0 + yl) * p.W + tc.x0 + xl);
+            const float scale_g = p.inv_scale * kActGain, nz_g = nz * kActGain;
             float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
             for (int j = 0; j < chunks; ++j) {
                 uint32_t v[32];
@@ -394,10 +460,16 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                     if (lane == 0) mbar_arrive(empty_acc(acc));
                 }
                 float o[32];
+                if (p.act) {                         // clamp(lrelu(f) * sqrt2) with the gain folded into the scale
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float f = __uint_as_float(v[i]) * p.inv_scale + nz;
-                    o[i] = p.act ? lrelu_agc(f) : f;
+                    for (int i = 0; i < 32; ++i) {
+                        float t = fmaf(__uint_as_float(v[i]), scale_g, nz_g);
+                        t = fmaxf(t, t * kLreluAlpha);
+                        o[i] = fminf(fmaxf(t, -kActClamp), kActClamp);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = fmaf(__uint_as_float(v[i]), p.inv_scale, nz);
                 }
                 if (p.torgb) {                       // 1x1 conv Cout -> 3 on the activated row (weights broadcast from smem)
                     const float4* w0 = reinterpret_cast<const float4*>(s_rgb + j * 32);
@@ -467,9 +539,6 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
         // ================================ prologue (depthwise) ========================
         const int g = (warp - kProWarp0) >> 2;            // channel half of the K-block this group produces
         const int tg = threadIdx.x - (kProWarp0 * 32 + g * 128);
-        const int ncols = p.tile_n * p.tile_w;
-        const int th = p.tile_h, tw = p.tile_w;
-        const int row_f4 = (tw + 2) * 8;                  // float4 per halo'd input row (32 ch = 8 float4 / pixel)
         for (int it = 0; it < my_tiles; ++it) {
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int kbc = it * num_kb + kb;
@@ -481,41 +550,10 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                 const float4* sin = reinterpret_cast<const float4*>(smem_gen + p.off_in + s * p.in_stage_stride);
                 uint8_t* a_hi = smem_gen + p.off_a + sa * kAStage;
                 uint8_t* a_lo = a_hi + kABytes;
-                for (int item = tg; item < ncols * 8; item += 128) {
-                    const int cvec = item & 7, colidx = item >> 3;
-                    const int col = (colidx & 3) * (ncols >> 2) + (colidx >> 2);
-                    const int img_l = col / tw, x = col - img_l * tw;
-                    const int cg = kb * kKBlock + g * kChunkC + cvec * 4;
-                    float4 w[9];
-#pragma unroll
-                    for (int t = 0; t < 9; ++t) w[t] = ldg4(p.w9 + t * p.cin + cg);
-                    const float4 bv = ldg4(p.bias + cg);
-                    const float4* base = sin + (img_l * (th + 2) * (tw + 2) + x) * 8 + cvec;
-                    float4 r0[3], r1[3], r2[3];
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) { r0[d] = base[d * 8]; r1[d] = base[row_f4 + d * 8]; }
-                    const uint32_t jchunk = (uint32_t)(g * 4 + (cvec >> 1));
-                    const uint32_t sub = (uint32_t)(cvec & 1) * 8;
-                    for (int y = 0; y < th; ++y) {
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) r2[d] = base[(y + 2) * row_f4 + d * 8];
-                        float4 a = bv;
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) { fma4(a, w[d], r0[d]); fma4(a, w[3 + d], r1[d]); fma4(a, w[6 + d], r2[d]); }
-                        a = lrelu_agc4(a);
-                        __half h[4], l[4];
-                        split_f16(a.x, kActSplitScale, h[0], l[0]);
-                        split_f16(a.y, kActSplitScale, h[1], l[1]);
-                        split_f16(a.z, kActSplitScale, h[2], l[2]);
-                        split_f16(a.w, kActSplitScale, h[3], l[3]);
-                        const int m = (img_l * th + y) * tw + x;
-                        const uint32_t off = (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u + ((jchunk ^ (uint32_t)(m & 7)) << 4) + sub;
-                        *reinterpret_cast<uint2*>(a_hi + off) = *reinterpret_cast<uint2*>(h);
-                        *reinterpret_cast<uint2*>(a_lo + off) = *reinterpret_cast<uint2*>(l);
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) { r0[d] = r1[d]; r1[d] = r2[d]; }
-                    }
-                }
+                const int cg0 = kb * kKBlock + g * kChunkC;
+                if (p.tile_w == 16) prologue_chunk<1, 8, 16>(sin, a_hi, a_lo, p.w9, p.bias, p.cin, cg0, g, tg);
+                else if (p.tile_w == 8) prologue_chunk<2, 8, 8>(sin, a_hi, a_lo, p.w9, p.bias, p.cin, cg0, g, tg);
+                else prologue_chunk<8, 4, 4>(sin, a_hi, a_lo, p.w9, p.bias, p.cin, cg0, g, tg);
                 fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) {
