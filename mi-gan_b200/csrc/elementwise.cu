@@ -118,70 +118,106 @@ cudaError_t launch_dw3x3(const float* in, const float* w9, const float* bias, fl
 }
 
 // --------------------------------------------------------------------------------------
-// depthwise 3x3 + bias + act + FIR 4x4 / stride 2 / pad 1.  One thread = one low-res output
-// pixel x 4 channels: it evaluates the 4x4 activated depthwise outputs the FIR needs from a
-// 6x6 input window (L1-served 128-bit loads; no block-level staging or barriers, so many warps
-// stay in flight).  Depthwise outputs outside the image are ZERO (the FIR zero-pads the
-// ACTIVATED tensor, migan_inference.py:62-70), not act(bias).
+// depthwise 3x3 + bias + act + FIR 4x4 / stride 2 / pad 1 (SeparableConv2d.conv1 + Downsample2d).
+//
+// Thread = (channel PAIR, low-res column ox, strip of RS low-res rows).  It walks down the hi-res
+// input rows once, keeping a rolling 3-row x 6-column window in registers (L1-served 64-bit loads,
+// a warp reads 256 contiguous bytes per pixel), evaluates each activated depthwise value of its 4
+// columns exactly once per row and scatters it into the two FIR accumulators it contributes to
+// (rows 2oy-1..2oy+2 feed output oy).  All MACs are packed FFMA2 (two channels per instruction).
+// Depthwise outputs outside the image are ZERO (the FIR zero-pads the ACTIVATED tensor,
+// migan_inference.py:62-70), not act(bias).
 // --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 3)
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
+    return d;
+}
+__device__ __forceinline__ float2 unpk2(u64 v) {
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+    return make_float2(__uint_as_float(lo), __uint_as_float(hi));
+}
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 ldg2(const float* p) { return __ldg(reinterpret_cast<const unsigned long long*>(p)); }
+__device__ __forceinline__ u64 lrelu_agc2(u64 v) {
+    const float2 a = unpk2(v);
+    return pk2(lrelu_agc(a.x), lrelu_agc(a.y));
+}
+
+// RS = low-res rows per thread (template: the row walk is fully unrolled so the rolling window stays in registers)
+template <int RS>
+__global__ void __launch_bounds__(256, 2)
 dw3x3_down_kernel(const float* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ bias,
                   const float* __restrict__ fir16, float* __restrict__ out_f32,
-                  __half* __restrict__ out_hi, __half* __restrict__ out_lo, uint32_t items, int lw2, int lh2, int lcv) {
-    const uint32_t idx = blockIdx.x * 128u + threadIdx.x;
+                  __half* __restrict__ out_hi, __half* __restrict__ out_lo, uint32_t items, int lw2, int lh2, int lcp, int lstrips) {
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
     if (idx >= items) return;
-    const int W2 = 1 << lw2, H2 = 1 << lh2, W = 2 * W2, H = 2 * H2, C = 4 << lcv;
-    const int c = (int)(idx & ((1u << lcv) - 1)) * 4;
-    const uint32_t p = idx >> lcv;                       // low-res pixel index over the image group
-    const int ox = (int)(p & (W2 - 1));
-    const int oy = (int)((p >> lw2) & (H2 - 1));
-    const size_t img = p >> (lw2 + lh2);
+    const int W2 = 1 << lw2, H2 = 1 << lh2, W = 2 * W2, H = 2 * H2, C = 2 << lcp;
+    const int c = (int)(idx & ((1u << lcp) - 1)) * 2;
+    uint32_t t = idx >> lcp;
+    const int ox = (int)(t & (W2 - 1));
+    t >>= lw2;
+    const int strip = (int)(t & ((1u << lstrips) - 1));
+    const size_t img = t >> lstrips;
+    constexpr int rs = RS;
+    const int oy0 = strip * rs;
     const float* src = in + img * (size_t)H * W * C + c;
-    float4 wv[9];
+    u64 wv[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wv[t] = ldg4(w9 + t * C + c);
-    const float4 bv = ldg4(bias + c);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    // input rows 2*oy-2 .. 2*oy+3, columns 2*ox-2 .. 2*ox+3; rolling 3-row window of 6 columns
-    float4 r[3][6];
-    const int ix0 = 2 * ox - 2, iy0 = 2 * oy - 2;
+    for (int k = 0; k < 9; ++k) wv[k] = ldg2(w9 + k * C + c);
+    const u64 bv = ldg2(bias + c);
+    const int ix0 = 2 * ox - 2;
+    u64 r[3][6];                                          // rolling input window: rows (iy-2, iy-1, iy) x 6 columns
     auto load_row = [&](int slot, int iy) {
+        const bool rowok = (iy >= 0 && iy < H);
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             const int ix = ix0 + j;
-            r[slot][j] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? ldg4(src + ((size_t)iy * W + ix) * C)
-                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            r[slot][j] = (rowok && ix >= 0 && ix < W) ? ldg2(src + ((size_t)iy * W + ix) * C) : 0ull;
         }
     };
-    load_row(0, iy0);
-    load_row(1, iy0 + 1);
+    const int iy_first = 2 * oy0 - 2;
+    load_row(0, iy_first);
+    load_row(1, iy_first + 1);
+    u64 accA = 0ull, accB = 0ull;                         // FIR accumulators of output rows k-1 and k
+    // depthwise rows gy = 2*oy0-1 .. 2*(oy0+rs-1)+2 ; gy = 2k-1 / 2k contribute taps (0 | 2) / (1 | 3) to rows (k | k-1)
 #pragma unroll
-    for (int ty = 0; ty < 4; ++ty) {                     // depthwise output row 2*oy-1+ty
-        load_row((ty + 2) % 3, iy0 + ty + 2);
-        const int gy = 2 * oy - 1 + ty;
-        if (gy < 0 || gy >= H) continue;
+    for (int q = 0; q < 2 * rs + 2; ++q) {
+        const int gy = 2 * oy0 - 1 + q;
+        load_row((q + 2) % 3, gy + 1);
+        const int k = (gy + 1) >> 1;                      // output row that starts (gy odd) or continues (gy even) here
+        const int tyB = (q & 1) ? 1 : 0;                  // tap row for output k   (gy = 2*oy0-1+q is odd iff q is even)
+        const int tyA = tyB + 2;                          // tap row for output k-1
+        if (gy >= 0 && gy < H) {
 #pragma unroll
-        for (int tx = 0; tx < 4; ++tx) {                 // depthwise output column 2*ox-1+tx
-            const int gx = 2 * ox - 1 + tx;
-            if (gx < 0 || gx >= W) continue;
-            float4 d = bv;
+            for (int tx = 0; tx < 4; ++tx) {
+                const int gx = 2 * ox - 1 + tx;
+                if (gx < 0 || gx >= W) continue;
+                u64 d = bv;
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+                for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) fma4(d, wv[ky * 3 + kx], r[(ty + ky) % 3][tx + kx]);
-            fma4(acc, ldg4(fir16 + (ty * 4 + tx) * C + c), lrelu_agc4(d));
+                    for (int kx = 0; kx < 3; ++kx) d = ffma2(wv[ky * 3 + kx], r[(q + ky) % 3][tx + kx], d);
+                d = lrelu_agc2(d);
+                accB = ffma2(ldg2(fir16 + (tyB * 4 + tx) * C + c), d, accB);
+                accA = ffma2(ldg2(fir16 + (tyA * 4 + tx) * C + c), d, accA);
+            }
         }
-    }
-    const size_t o = (size_t)p * C + c;
-    if (out_f32) stg4(out_f32 + o, acc);
-    if (out_hi) {
-        __half h[4], l[4];
-        split_f16(acc.x, kActSplitScale, h[0], l[0]);
-        split_f16(acc.y, kActSplitScale, h[1], l[1]);
-        split_f16(acc.z, kActSplitScale, h[2], l[2]);
-        split_f16(acc.w, kActSplitScale, h[3], l[3]);
-        *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(h);
-        *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(l);
+        if ((q & 1) && q >= 3) {                          // gy = 2k even: last contribution (tap 3) to output row k-1 of this strip
+            const size_t o = ((img * H2 + (k - 1)) * W2 + ox) * (size_t)C + c;
+            const float2 v = unpk2(accA);
+            if (out_f32) *reinterpret_cast<float2*>(out_f32 + o) = v;
+            if (out_hi) {
+                __half h0, l0, h1, l1;
+                split_f16(v.x, kActSplitScale, h0, l0);
+                split_f16(v.y, kActSplitScale, h1, l1);
+                *reinterpret_cast<__half2*>(out_hi + o) = __halves2half2(h0, h1);
+                *reinterpret_cast<__half2*>(out_lo + o) = __halves2half2(l0, l1);
+            }
+        }
+        if (q & 1) { accA = accB; accB = 0ull; }          // row k becomes "k-1" for the next pair of depthwise rows
     }
 }
 
@@ -191,13 +227,15 @@ cudaError_t launch_dw3x3_down(const float* in, const float* w9, const float* bia
                               float* out_f32, __half* out_hi, __half* out_lo,
                               int n, int H, int W, int C, cudaStream_t s) {
     const int H2 = H / 2, W2 = W / 2;
-    const size_t per_img = (size_t)H2 * W2 * (C / 4);
+    const int rs = (H2 >= 8) ? 8 : 4, strips = H2 / rs;
+    const size_t per_img = (size_t)strips * W2 * (C / 2);
     return for_image_groups(n, per_img, [&](int i0, int cnt) {
         const uint32_t items = (uint32_t)(per_img * cnt);
         const size_t oi = (size_t)i0 * H * W * C, oo = (size_t)i0 * H2 * W2 * C;
-        dw3x3_down_kernel<<<(items + 127) / 128, 128, 0, s>>>(in + oi, w9, bias, fir16, out_f32 ? out_f32 + oo : nullptr,
-                                                             out_hi ? out_hi + oo : nullptr, out_lo ? out_lo + oo : nullptr,
-                                                             items, host_log2(W2), host_log2(H2), host_log2(C / 4));
+        auto kern = (rs == 8) ? dw3x3_down_kernel<8> : dw3x3_down_kernel<4>;
+        kern<<<(items + 255) / 256, 256, 0, s>>>(in + oi, w9, bias, fir16, out_f32 ? out_f32 + oo : nullptr,
+                                                out_hi ? out_hi + oo : nullptr, out_lo ? out_lo + oo : nullptr,
+                                                items, host_log2(W2), host_log2(H2), host_log2(C / 2), host_log2(strips));
     });
 }
 

@@ -882,6 +882,12 @@ int migan_tap_info(const migan_ctx* ctx, int path, int index, const char** name,
     return MIGAN_OK;
 }
 
+int migan_debug_read_tc_trace(unsigned long long* host_4096) {
+    cudaError_t e = migan::sepconv_tc_read_trace(host_4096);
+    if (e != cudaSuccess) return fail(MIGAN_ERR_CUDA, "trace read failed: %s", cudaGetErrorString(e));
+    return MIGAN_OK;
+}
+
 int b200_upfirdn2d(const float* x, const float* f, float* y, int n, int c, int h, int w, int fh, int fw,
                    int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1,
                    int flip_filter, float gain, void* stream) {

@@ -34,6 +34,7 @@ const char* sepconv_tc_plan(SepconvTcArgs* a, int passes, const float* in_f32, c
                             const float* w9, const float* bias, const __half* w_hi, const __half* w_lo,
                             float inv_scale, const float* noise, float* out, int n, int res, int cin, int cout, int act,
                             const SepconvTcRgb* rgb = nullptr);
+cudaError_t sepconv_tc_read_trace(unsigned long long* host_4096);
 cudaError_t launch_sepconv_tc(const SepconvTcArgs& a, cudaStream_t s, float* img_out_override = nullptr);
 
 }  // namespace migan
