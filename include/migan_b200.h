@@ -11,6 +11,7 @@
  *   migan_forward_host                scripts/demo.py:131-136 (x.to(device) -> model(x) -> .cpu())
  *   b200_upfirdn2d                    _plugin.upfirdn2d(...)        torch_utils/ops/upfirdn2d.cpp:16-94
  *   b200_bias_act                     _plugin.bias_act(...)         torch_utils/ops/bias_act.cpp:32-90 (grad == 0)
+ *   b200_conv1x1_nhwc                 the F.conv2d of conv2d_resample's 1x1 branches  torch_utils/ops/conv2d_resample.py:106-116
  *
  * Conventions: every function returns 0 on success and a non-zero code on failure, after
  * which migan_last_error() describes the failure (thread-local string).  All device pointers
@@ -106,6 +107,11 @@ int migan_debug_read_tc_trace(unsigned long long* host_4096);
 int b200_upfirdn2d(const float* x, const float* f, float* y, int n, int c, int h, int w, int fh, int fw,
                    int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1,
                    int flip_filter, float gain, void* stream);
+
+/* 1x1 convolution on channels-last data: y[p][o] = sum_i x[p][i] * w_t[i][o]  (fp32 CUDA-core GEMM;
+ * the conv inside conv2d_resample's 1x1 branches, torch_utils/ops/conv2d_resample.py:106-116).
+ * cin % 16 == 0, cout % 64 == 0. */
+int b200_conv1x1_nhwc(const float* x, const float* w_t, float* y, int64_t pixels, int cin, int cout, void* stream);
 
 /* bias_act forward: y = clamp(gain * act(x + b)), b indexed along the dimension whose stride is
  * step_b and size size_b (bias_act.cpp:72-73: (xi / stepB) % sizeB); b == NULL: no bias.

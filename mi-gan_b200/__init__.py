@@ -8,8 +8,8 @@ Public surface (mirrors the reference's for this path):
 
 The directory is named `mi-gan_b200`; import it as `migan_b200` (repo-root shim `migan_b200.py`).
 """
-from . import arch, build  # noqa: F401
+from . import arch, build, ops, parallel, synthetic  # noqa: F401
 from .generator import Generator  # noqa: F401
 
-__all__ = ["Generator", "arch", "build"]
+__all__ = ["Generator", "arch", "build", "ops", "parallel", "synthetic"]
 __version__ = "0.1.0"

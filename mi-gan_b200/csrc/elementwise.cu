@@ -141,9 +141,13 @@ __device__ __forceinline__ float2 unpk2(u64 v) {
 }
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ u64 ldg2(const float* p) { return __ldg(reinterpret_cast<const unsigned long long*>(p)); }
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// lrelu_agc on a channel pair, bit-identical to the scalar form: max(v, 0.2 v) == leaky_relu(v) exactly,
+// then * sqrt2 and clamp; the two multiplies run packed.
 __device__ __forceinline__ u64 lrelu_agc2(u64 v) {
-    const float2 a = unpk2(v);
-    return pk2(lrelu_agc(a.x), lrelu_agc(a.y));
+    const float2 a = unpk2(v), b = unpk2(fmul2(v, pk2(kLreluAlpha, kLreluAlpha)));
+    const float2 m = unpk2(fmul2(pk2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)), pk2(kActGain, kActGain)));
+    return pk2(fminf(fmaxf(m.x, -kActClamp), kActClamp), fminf(fmaxf(m.y, -kActClamp), kActClamp));
 }
 
 // RS = low-res rows per thread (template: the row walk is fully unrolled so the rolling window stays in registers)

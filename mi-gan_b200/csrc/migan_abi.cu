@@ -913,6 +913,16 @@ int b200_upfirdn2d(const float* x, const float* f, float* y, int n, int c, int h
     return MIGAN_OK;
 }
 
+int b200_conv1x1_nhwc(const float* x, const float* w_t, float* y, int64_t pixels, int cin, int cout, void* stream) {
+    if (pixels < 0 || (pixels > 0 && (!x || !w_t || !y))) return fail(MIGAN_ERR_INVALID, "null tensor");
+    if (cin % 16 != 0 || cout % 64 != 0 || cin < 16 || cout < 64)
+        return fail(MIGAN_ERR_INVALID, "conv1x1: cin must be a multiple of 16 and cout of 64, got %d -> %d", cin, cout);
+    if (pixels == 0) return MIGAN_OK;
+    cudaError_t e = migan::launch_pw_gemm_simt(x, w_t, y, pixels, cin, cout, nullptr, 1, 0, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(MIGAN_ERR_CUDA, "conv1x1 launch failed: %s", cudaGetErrorString(e));
+    return MIGAN_OK;
+}
+
 int b200_bias_act(const float* x, const float* b, float* y, int64_t numel, int64_t step_b, int size_b,
                   int act, float alpha, float gain, float clamp, void* stream) {
     if (numel < 0 || (numel > 0 && (!x || !y))) return fail(MIGAN_ERR_INVALID, "null tensor");

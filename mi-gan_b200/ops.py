@@ -1,0 +1,217 @@
+"""sm_100a drop-ins for the reference's `torch_utils/ops` used around the generator path:
+`upfirdn2d` (+ `setup_filter`, `filter2d`, `upsample2d`, `downsample2d`), `bias_act` and the 1x1
+branches of `conv2d_resample`.  Same function names, argument meaning and error behaviour as the
+reference (torch_utils/ops/upfirdn2d.py:72-384, bias_act.py:55-89, conv2d_resample.py:59-154);
+forward only (inference), float32 NCHW CUDA tensors, no `impl='ref'` / CPU fallback -- the CPU
+oracles live in oracle/ for the tests.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _abi
+
+# name -> (cuda_idx, def_alpha, def_gain)   torch_utils/ops/bias_act.py:22-32
+ACTIVATIONS = {
+    "linear": (1, 0.0, 1.0), "relu": (2, 0.0, float(np.sqrt(2))), "lrelu": (3, 0.2, float(np.sqrt(2))),
+    "tanh": (4, 0.0, 1.0), "sigmoid": (5, 0.0, 1.0), "elu": (6, 0.0, 1.0), "selu": (7, 0.0, 1.0),
+    "softplus": (8, 0.0, 1.0), "swish": (9, 0.0, float(np.sqrt(2))),
+}
+
+
+def _stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda_f32(x: torch.Tensor, what: str) -> torch.Tensor:
+    if not isinstance(x, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % what)
+    if not x.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: migan_b200.ops has no CPU path" % what)
+    if x.dtype != torch.float32:
+        raise RuntimeError("%s must be float32, got %s" % (what, x.dtype))
+    return x.contiguous()
+
+
+def _parse_scaling(scaling):
+    if isinstance(scaling, int):
+        scaling = [scaling, scaling]
+    assert isinstance(scaling, (list, tuple)) and all(isinstance(v, int) for v in scaling)
+    sx, sy = scaling
+    assert sx >= 1 and sy >= 1
+    return sx, sy
+
+
+def _parse_padding(padding):
+    if isinstance(padding, int):
+        padding = [padding, padding]
+    assert isinstance(padding, (list, tuple)) and all(isinstance(v, int) for v in padding)
+    if len(padding) == 2:
+        px, py = padding
+        padding = [px, px, py, py]
+    padx0, padx1, pady0, pady1 = padding
+    return padx0, padx1, pady0, pady1
+
+
+def _get_filter_size(f):
+    if f is None:
+        return 1, 1
+    assert isinstance(f, torch.Tensor) and f.ndim in [1, 2]
+    return int(f.shape[-1]), int(f.shape[0])
+
+
+def setup_filter(f, device=torch.device("cpu"), normalize=True, flip_filter=False, gain=1, separable=None):
+    """FIR prototype -> filter tensor (torch_utils/ops/upfirdn2d.py:72-116)."""
+    if f is None:
+        f = 1
+    f = torch.as_tensor(f, dtype=torch.float32)
+    assert f.ndim in [0, 1, 2] and f.numel() > 0
+    if f.ndim == 0:
+        f = f[None]
+    if separable is None:
+        separable = (f.ndim == 1 and f.numel() >= 8)
+    if f.ndim == 1 and not separable:
+        f = torch.outer(f, f)
+    assert f.ndim == (1 if separable else 2)
+    if normalize:
+        f = f / f.sum()
+    if flip_filter:
+        f = f.flip(list(range(f.ndim)))
+    f = f * (gain ** (f.ndim / 2))
+    return f.to(device=device)
+
+
+def _upfirdn2d_pass(x, f2d, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
+    lib = _abi.load()
+    n, c, h, w = x.shape
+    fh, fw = f2d.shape
+    ow = (w * upx + padx0 + padx1 - fw + downx) // downx   # upfirdn2d.cpp:32-33
+    oh = (h * upy + pady0 + pady1 - fh + downy) // downy
+    if ow < 1 or oh < 1:
+        raise RuntimeError("upfirdn2d: output size must be >= 1, got %dx%d" % (oh, ow))
+    y = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _abi.check(lib.b200_upfirdn2d(x.data_ptr(), f2d.data_ptr(), y.data_ptr(), n, c, h, w, fh, fw, upx, upy, downx, downy,
+                                      padx0, padx1, pady0, pady1, int(bool(flip)), float(gain), _stream(x)))
+    return y
+
+
+def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl="cuda"):
+    """Pad, zero-insert up-sample, FIR filter, decimate (torch_utils/ops/upfirdn2d.py:120-164)."""
+    assert impl == "cuda", "migan_b200.ops has no reference/CPU implementation (see oracle/)"
+    x = _require_cuda_f32(x, "x")
+    if x.ndim != 4:
+        raise RuntimeError("x must be rank 4 [N,C,H,W]")
+    upx, upy = _parse_scaling(up)
+    downx, downy = _parse_scaling(down)
+    padx0, padx1, pady0, pady1 = _parse_padding(padding)
+    if f is None:
+        f = torch.ones([1, 1], dtype=torch.float32, device=x.device)
+    assert isinstance(f, torch.Tensor) and f.ndim in [1, 2] and f.dtype == torch.float32
+    f = f.to(x.device).contiguous()
+    if f.ndim == 2:
+        return _upfirdn2d_pass(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip_filter, gain)
+    # separable: two 1-D passes, sqrt(gain) each (upfirdn2d.py:238-240)
+    y = _upfirdn2d_pass(x, f.unsqueeze(0).contiguous(), upx, 1, downx, 1, padx0, padx1, 0, 0, flip_filter, np.sqrt(gain))
+    return _upfirdn2d_pass(y, f.unsqueeze(1).contiguous(), 1, upy, 1, downy, 0, 0, pady0, pady1, flip_filter, np.sqrt(gain))
+
+
+def filter2d(x, f, padding=0, flip_filter=False, gain=1, impl="cuda"):
+    """upfirdn2d.py:272-304."""
+    padx0, padx1, pady0, pady1 = _parse_padding(padding)
+    fw, fh = _get_filter_size(f)
+    p = [padx0 + fw // 2, padx1 + (fw - 1) // 2, pady0 + fh // 2, pady1 + (fh - 1) // 2]
+    return upfirdn2d(x, f, padding=p, flip_filter=flip_filter, gain=gain, impl=impl)
+
+
+def upsample2d(x, f, up=2, padding=0, flip_filter=False, gain=1, impl="cuda"):
+    """upfirdn2d.py:308-343."""
+    upx, upy = _parse_scaling(up)
+    padx0, padx1, pady0, pady1 = _parse_padding(padding)
+    fw, fh = _get_filter_size(f)
+    p = [padx0 + (fw + upx - 1) // 2, padx1 + (fw - upx) // 2, pady0 + (fh + upy - 1) // 2, pady1 + (fh - upy) // 2]
+    return upfirdn2d(x, f, up=up, padding=p, flip_filter=flip_filter, gain=gain * upx * upy, impl=impl)
+
+
+def downsample2d(x, f, down=2, padding=0, flip_filter=False, gain=1, impl="cuda"):
+    """upfirdn2d.py:347-382."""
+    downx, downy = _parse_scaling(down)
+    padx0, padx1, pady0, pady1 = _parse_padding(padding)
+    fw, fh = _get_filter_size(f)
+    p = [padx0 + (fw - downx + 1) // 2, padx1 + (fw - downx) // 2, pady0 + (fh - downy + 1) // 2, pady1 + (fh - downy) // 2]
+    return upfirdn2d(x, f, down=down, padding=p, flip_filter=flip_filter, gain=gain, impl=impl)
+
+
+def bias_act(x, b=None, dim=1, act="linear", alpha=None, gain=None, clamp=None, impl="cuda"):
+    """Fused bias + activation + gain + clamp, forward only (torch_utils/ops/bias_act.py:55-89)."""
+    assert impl == "cuda", "migan_b200.ops has no reference/CPU implementation (see oracle/)"
+    x = _require_cuda_f32(x, "x")
+    if act not in ACTIVATIONS:
+        raise KeyError(act)
+    idx, def_alpha, def_gain = ACTIVATIONS[act]
+    alpha = float(def_alpha if alpha is None else alpha)
+    gain = float(def_gain if gain is None else gain)
+    assert clamp is None or clamp >= 0
+    clamp = float(-1 if clamp is None else clamp)
+    step_b, size_b, bptr = 1, 1, None
+    if b is not None:
+        b = _require_cuda_f32(b, "b")
+        assert b.ndim == 1 and 0 <= dim < x.ndim and b.shape[0] == x.shape[dim]
+        step_b = int(np.prod(x.shape[dim + 1:])) if dim + 1 < x.ndim else 1
+        size_b = int(b.shape[0])
+        bptr = b.data_ptr()
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _abi.check(_abi.load().b200_bias_act(x.data_ptr(), bptr, y.data_ptr(), x.numel(), step_b, size_b, idx, alpha, gain, clamp,
+                                             _stream(x)))
+    return y
+
+
+def _conv1x1(x, w):
+    """y[n,o,h,w] = sum_i w[o,i] x[n,i,h,w] on the CUDA-core GEMM (NHWC inside; the layout change is torch plumbing)."""
+    n, ci, h, wd = x.shape
+    co = w.shape[0]
+    xa = x.permute(0, 2, 3, 1).contiguous()
+    wt = w.reshape(co, ci).t().contiguous()
+    y = torch.empty((n, h, wd, co), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _abi.check(_abi.load().b200_conv1x1_nhwc(xa.data_ptr(), wt.data_ptr(), y.data_ptr(), n * h * wd, ci, co, _stream(x)))
+    return y.permute(0, 3, 1, 2).contiguous()
+
+
+def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
+    """2-D convolution with optional up/down-sampling (torch_utils/ops/conv2d_resample.py:59-154).
+    Implemented: the 1x1-kernel branches the MI-GAN graph uses (:106-116 and the plain case :145-147).
+    k x k kernels (Co-Mod-GAN teacher) are not built yet and raise NotImplementedError."""
+    x = _require_cuda_f32(x, "x")
+    w = _require_cuda_f32(w, "w")
+    assert x.ndim == 4 and w.ndim == 4
+    assert isinstance(up, int) and up >= 1 and isinstance(down, int) and down >= 1 and groups >= 1
+    out_channels, in_channels_per_group, kh, kw = w.shape
+    fw, fh = _get_filter_size(f)
+    px0, px1, py0, py1 = _parse_padding(padding)
+    if up > 1:   # conv2d_resample.py:94-98
+        px0 += (fw + up - 1) // 2; px1 += (fw - up) // 2; py0 += (fh + up - 1) // 2; py1 += (fh - up) // 2
+    if down > 1:  # :101-104
+        px0 += (fw - down + 1) // 2; px1 += (fw - down) // 2; py0 += (fh - down + 1) // 2; py1 += (fh - down) // 2
+    if kh != 1 or kw != 1 or groups != 1:
+        raise NotImplementedError("migan_b200.ops.conv2d_resample: only 1x1 kernels with groups=1 are built (MI-GAN path)")
+    if x.shape[1] % 4 or out_channels % 64 or x.shape[1] % 16:
+        raise NotImplementedError("conv2d_resample 1x1: Cin must be a multiple of 16 and Cout of 64")
+    if down > 1 and up == 1:    # :106-110  FIR-down, then conv
+        x = upfirdn2d(x, f, down=down, padding=[px0, px1, py0, py1], flip_filter=flip_filter)
+        return _conv1x1(x, w)
+    if up > 1 and down == 1:    # :113-116  conv, then FIR-up with gain up^2
+        x = _conv1x1(x, w)
+        return upfirdn2d(x, f, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
+    if up == 1 and down == 1 and [px0, px1, py0, py1] == [0, 0, 0, 0]:   # :145-147
+        return _conv1x1(x, w)
+    # generic fallback order (:150-154): up-FIR, conv, down-sample
+    x = upfirdn2d(x, (f if up > 1 else None), up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
+    x = _conv1x1(x, w)
+    if down > 1:
+        x = upfirdn2d(x, f, down=down, flip_filter=flip_filter)
+    return x
