@@ -84,7 +84,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()
@@ -300,8 +300,16 @@ def run_b200(args):
     peak, peak_src = measured_peaks()
     d = by_kernel[dom]
     achieved = d["alg_bytes"] / (d["ms"] * 1e-3) / 1e9
+    traffic, traffic_note = None, None
+    try:  # DRAM bytes of one profiled launch of the dominant kernel (ncu --set full), committed under profiles/
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f).get(dom)
+        if tj:
+            traffic, traffic_note = tj["dram_bytes"], tj
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_launch": traffic_note, "peak_source": peak_src,
                 "launches_per_step": d["launches"], "share_of_step": d["ms"] / total_ms,
                 "whole_step": {"alg_bytes": sum(b["alg_bytes"] for b in by_kernel.values()), "ms_sum_of_kernels": total_ms,
                                "GBps": sum(b["alg_bytes"] for b in by_kernel.values()) / (total_ms * 1e-3) / 1e9},
