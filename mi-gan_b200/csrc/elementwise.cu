@@ -27,30 +27,43 @@ static inline unsigned blocks_for(int64_t items, int threads) {
 // (64-bit div/mod costs ~100 instructions per thread and dominated these kernels otherwise).
 __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 
+// Thread = (4 output channels, 4 adjacent pixels): the 4x4 weights + bias stay in registers, x is read as one
+// 128-bit load per input plane, and the thread writes four 128-bit vectors (each warp instruction covers whole
+// 256-byte pixel rows).  The first version re-loaded weights per output vector and saturated the L1 (ncu: L1/TEX
+// throughput 99 %, DRAM 21 %).
 __global__ void __launch_bounds__(256)
 stem_fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                     float* __restrict__ out, uint32_t items, int lhw, int lcv) {
-    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;     // over (pixel quads) x (channel quads)
     if (idx >= items) return;
     const uint32_t c4 = idx & ((1u << lcv) - 1);
-    const uint32_t p = idx >> lcv;
+    const uint32_t pq = idx >> lcv;                           // pixel-quad index over the image group
+    const uint32_t p = pq << 2;
     const uint32_t q = p & ((1u << lhw) - 1);
     const uint32_t img = p >> lhw;
     const size_t HW = (size_t)1 << lhw;
     const float* xp = x + (size_t)img * 4 * HW + q;
-    const float x0 = __ldg(xp), x1 = __ldg(xp + HW), x2 = __ldg(xp + 2 * HW), x3 = __ldg(xp + 3 * HW);
-    float o[4];
+    const float4 x0 = ldg4(xp), x1 = ldg4(xp + HW), x2 = ldg4(xp + 2 * HW), x3 = ldg4(xp + 3 * HW);
+    float4 wc[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = c4 * 4 + j;
-        const float4 wc = ldg4(w + c * 4);
-        float v = wc.x * x0;
-        v = fmaf(wc.y, x1, v);
-        v = fmaf(wc.z, x2, v);
-        v = fmaf(wc.w, x3, v);
-        o[j] = lrelu_agc(v + __ldg(b + c));
+    for (int j = 0; j < 4; ++j) wc[j] = ldg4(w + (c4 * 4 + j) * 4);
+    const float4 bv = ldg4(b + c4 * 4);
+    const float bj[4] = {bv.x, bv.y, bv.z, bv.w};
+    const float px[4][4] = {{x0.x, x1.x, x2.x, x3.x}, {x0.y, x1.y, x2.y, x3.y}, {x0.z, x1.z, x2.z, x3.z}, {x0.w, x1.w, x2.w, x3.w}};
+    float* op = out + ((size_t)p << (lcv + 2)) + c4 * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = wc[j].x * px[i][0];
+            v = fmaf(wc[j].y, px[i][1], v);
+            v = fmaf(wc[j].z, px[i][2], v);
+            v = fmaf(wc[j].w, px[i][3], v);
+            o[j] = lrelu_agc(v + bj[j]);
+        }
+        stg4(op + ((size_t)i << (lcv + 2)), make_float4(o[0], o[1], o[2], o[3]));
     }
-    stg4(out + ((size_t)p << (lcv + 2)) + c4 * 4, make_float4(o[0], o[1], o[2], o[3]));
 }
 
 // Launch helper: split the batch so that one launch indexes < 2^31 work items.
@@ -69,7 +82,7 @@ static inline int host_log2(int v) { int l = 0; while ((1 << l) < v) ++l; return
 
 cudaError_t launch_stem(const float* x, const float* w, const float* b, float* out,
                         int n, int H, int W, int C0, cudaStream_t s) {
-    const size_t per_img = (size_t)H * W * (C0 / 4);
+    const size_t per_img = (size_t)H * W / 4 * (C0 / 4);
     return for_image_groups(n, per_img, [&](int i0, int cnt) {
         const uint32_t items = (uint32_t)(per_img * cnt);
         stem_fromrgb_kernel<<<(items + 255) / 256, 256, 0, s>>>(x + (size_t)i0 * 4 * H * W, w, b, out + (size_t)i0 * H * W * C0,
@@ -81,39 +94,76 @@ cudaError_t launch_stem(const float* x, const float* w, const float* b, float* o
 // depthwise 3x3 + bias + act, NHWC -> NHWC (used by the CUDA-core path; the tcgen05 path
 // fuses this stage into the GEMM prologue)
 // --------------------------------------------------------------------------------------
+// Thread = (4 channels, column x, strip of RS rows): the 9 taps + bias stay in registers and a 3x3 window slides
+// down the strip (3 L1-served 128-bit loads per output vector instead of 9 + 9 tap loads).
+template <int RS>
 __global__ void __launch_bounds__(256)
 dw3x3_act_kernel(const float* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ bias,
-                 float* __restrict__ out, uint32_t items, int lw, int lh, int lcv) {
+                 float* __restrict__ out, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                 uint32_t items, int lw, int lh, int lcv, int lstrips) {
     const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
     if (idx >= items) return;
     const int W = 1 << lw, H = 1 << lh, C = 4 << lcv;
     const int c = (int)(idx & ((1u << lcv) - 1)) * 4;
-    const uint32_t p = idx >> lcv;
-    const int x = (int)(p & (W - 1));
-    const int y = (int)((p >> lw) & (H - 1));
-    float4 acc = ldg4(bias + c);
+    uint32_t t = idx >> lcv;
+    const int x = (int)(t & (W - 1));
+    t >>= lw;
+    const int strip = (int)(t & ((1u << lstrips) - 1));
+    const size_t img = t >> lstrips;
+    const int y0 = strip * RS;
+    float4 w[9];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        const int yy = y + ky - 1;
-        if (yy < 0 || yy >= H) continue;
+    for (int k = 0; k < 9; ++k) w[k] = ldg4(w9 + k * C + c);
+    const float4 bv = ldg4(bias + c);
+    const float* base = in + img * (size_t)H * W * C + c;
+    const bool okl = x > 0, okr = x + 1 < W;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_row = [&](int y, float4 (&r)[3]) {
+        if (y < 0 || y >= H) { r[0] = r[1] = r[2] = zero; return; }
+        const float* p = base + ((size_t)y * W + x) * C;
+        r[0] = okl ? ldg4(p - C) : zero;
+        r[1] = ldg4(p);
+        r[2] = okr ? ldg4(p + C) : zero;
+    };
+    float4 r0[3], r1[3], r2[3], rn[3];
+    load_row(y0 - 1, r0);
+    load_row(y0, r1);
+    load_row(y0 + 1, r2);
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int xx = x + kx - 1;
-            if (xx < 0 || xx >= W) continue;
-            const size_t q = (size_t)((int64_t)p + (ky - 1) * W + (kx - 1));
-            fma4(acc, ldg4(w9 + (ky * 3 + kx) * C + c), ldg4(in + q * C + c));
+    for (int i = 0; i < RS; ++i) {
+        const int y = y0 + i;
+        if (i + 1 < RS) load_row(y + 2, rn);              // next iteration's bottom row: issued one iteration ahead
+        float4 acc = bv;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { fma4(acc, w[d], r0[d]); fma4(acc, w[3 + d], r1[d]); fma4(acc, w[6 + d], r2[d]); }
+        acc = lrelu_agc4(acc);
+        const size_t o = ((img * H + y) * (size_t)W + x) * C + c;
+        if (out) stg4(out + o, acc);
+        if (out_hi) {   // pre-split A operand for the tcgen05 GEMM (layers whose Cout spans several CTA N tiles)
+            __half h[4], l[4];
+            split_f16(acc.x, kActSplitScale, h[0], l[0]);
+            split_f16(acc.y, kActSplitScale, h[1], l[1]);
+            split_f16(acc.z, kActSplitScale, h[2], l[2]);
+            split_f16(acc.w, kActSplitScale, h[3], l[3]);
+            *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(h);
+            *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(l);
         }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { r0[d] = r1[d]; r1[d] = r2[d]; r2[d] = rn[d]; }
     }
-    stg4(out + (size_t)p * C + c, lrelu_agc4(acc));
 }
 
-cudaError_t launch_dw3x3(const float* in, const float* w9, const float* bias, float* out,
+cudaError_t launch_dw3x3(const float* in, const float* w9, const float* bias, float* out, __half* out_hi, __half* out_lo,
                          int n, int H, int W, int C, cudaStream_t s) {
-    const size_t per_img = (size_t)H * W * (C / 4);
+    const int rs = (H >= 8) ? 8 : 4, strips = H / rs;
+    const size_t per_img = (size_t)strips * W * (C / 4);
     return for_image_groups(n, per_img, [&](int i0, int cnt) {
         const uint32_t items = (uint32_t)(per_img * cnt);
         const size_t off = (size_t)i0 * H * W * C;
-        dw3x3_act_kernel<<<(items + 255) / 256, 256, 0, s>>>(in + off, w9, bias, out + off, items, host_log2(W), host_log2(H), host_log2(C / 4));
+        auto kern = (rs == 8) ? dw3x3_act_kernel<8> : dw3x3_act_kernel<4>;
+        kern<<<(items + 255) / 256, 256, 0, s>>>(in + off, w9, bias, out ? out + off : nullptr, out_hi ? out_hi + off : nullptr,
+                                                out_lo ? out_lo + off : nullptr, items, host_log2(W), host_log2(H), host_log2(C / 4),
+                                                host_log2(strips));
     });
 }
 
@@ -150,14 +200,17 @@ __device__ __forceinline__ u64 lrelu_agc2(u64 v) {
     return pk2(fminf(fmaxf(m.x, -kActClamp), kActClamp), fminf(fmaxf(m.y, -kActClamp), kActClamp));
 }
 
-// RS = low-res rows per thread (template: the row walk is fully unrolled so the rolling window stays in registers)
+// RS = low-res rows per thread (template: the row walk is fully unrolled).  Register plan per thread:
+//   in[6]      the current input row (columns 2ox-2 .. 2ox+3)
+//   dw[3][4]   partial depthwise sums of the three depthwise rows the current input row touches
+//   w[9], fir[16], bias  per-channel-pair constants;   6 column pointers advanced by one row per step
+// so every load is `[pointer]` with no index arithmetic, and each input row is read exactly once.
 template <int RS>
 __global__ void __launch_bounds__(256, 2)
 dw3x3_down_kernel(const float* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ bias,
                   const float* __restrict__ fir16, float* __restrict__ out_f32,
                   __half* __restrict__ out_hi, __half* __restrict__ out_lo, uint32_t items, int lw2, int lh2, int lcp, int lstrips) {
     const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
-    if (idx >= items) return;
     const int W2 = 1 << lw2, H2 = 1 << lh2, W = 2 * W2, H = 2 * H2, C = 2 << lcp;
     const int c = (int)(idx & ((1u << lcp) - 1)) * 2;
     uint32_t t = idx >> lcp;
@@ -165,63 +218,105 @@ dw3x3_down_kernel(const float* __restrict__ in, const float* __restrict__ w9, co
     t >>= lw2;
     const int strip = (int)(t & ((1u << lstrips) - 1));
     const size_t img = t >> lstrips;
-    constexpr int rs = RS;
-    const int oy0 = strip * rs;
-    const float* src = in + img * (size_t)H * W * C + c;
+    const int oy0 = strip * RS;
+
+    // FIR taps live in shared memory ([16][C], conflict-free 64-bit reads along the channel pairs): keeping them
+    // in registers (32 per thread) capped the kernel at 2 blocks / SM.
+    extern __shared__ float s_fir[];
+    for (int i = threadIdx.x; i < 16 * C; i += 256) s_fir[i] = __ldg(fir16 + i);
+    __syncthreads();
+    if (idx >= items) return;
+    const u64* firp = reinterpret_cast<const u64*>(s_fir + c);
+    const int fstride = C >> 1;                           // u64 elements between taps
     u64 wv[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) wv[k] = ldg2(w9 + k * C + c);
     const u64 bv = ldg2(bias + c);
-    const int ix0 = 2 * ox - 2;
-    u64 r[3][6];                                          // rolling input window: rows (iy-2, iy-1, iy) x 6 columns
-    auto load_row = [&](int slot, int iy) {
+
+    // column pointers / validity (columns 2ox-2 .. 2ox+3), positioned on input row 2*oy0-2
+    const int iy_first = 2 * oy0 - 2;
+    const float* colp[6];
+    bool colok[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const int ix = 2 * ox - 2 + j;
+        colok[j] = (ix >= 0 && ix < W);
+        colp[j] = in + ((img * H + iy_first) * (size_t)W + (colok[j] ? ix : 0)) * C + c;   // may point before the tensor: only dereferenced when valid
+    }
+    const size_t row_stride = (size_t)W * C;
+    bool dwok[4];
+#pragma unroll
+    for (int tx = 0; tx < 4; ++tx) dwok[tx] = (2 * ox - 1 + tx >= 0) && (2 * ox - 1 + tx < W);
+
+    u64 dw[3][4];                                         // dw[s]: partial sums of depthwise row (iy - 1 + s') ...
+#pragma unroll
+    for (int s2 = 0; s2 < 3; ++s2)
+#pragma unroll
+        for (int tx = 0; tx < 4; ++tx) dw[s2][tx] = bv;
+    u64 accA = 0ull, accB = 0ull;                         // FIR accumulators of output rows k-1 and k
+
+    // input rows r = 0 .. 2RS+3  (iy = iy_first + r); input row r completes depthwise row gy = iy - 1 (q = r - 2).
+    // The loads of row r+1 are issued before row r is consumed (software pipelining: ncu showed 44 % of the stalls
+    // on the scoreboard of loads used immediately after issue).
+    u64 vn[6];
+    auto fetch_row = [&](int r) {
+        const int iy = iy_first + r;
         const bool rowok = (iy >= 0 && iy < H);
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            const int ix = ix0 + j;
-            r[slot][j] = (rowok && ix >= 0 && ix < W) ? ldg2(src + ((size_t)iy * W + ix) * C) : 0ull;
+            vn[j] = (rowok && colok[j]) ? ldg2(colp[j]) : 0ull;
+            colp[j] += row_stride;
         }
     };
-    const int iy_first = 2 * oy0 - 2;
-    load_row(0, iy_first);
-    load_row(1, iy_first + 1);
-    u64 accA = 0ull, accB = 0ull;                         // FIR accumulators of output rows k-1 and k
-    // depthwise rows gy = 2*oy0-1 .. 2*(oy0+rs-1)+2 ; gy = 2k-1 / 2k contribute taps (0 | 2) / (1 | 3) to rows (k | k-1)
+    fetch_row(0);
 #pragma unroll
-    for (int q = 0; q < 2 * rs + 2; ++q) {
-        const int gy = 2 * oy0 - 1 + q;
-        load_row((q + 2) % 3, gy + 1);
-        const int k = (gy + 1) >> 1;                      // output row that starts (gy odd) or continues (gy even) here
-        const int tyB = (q & 1) ? 1 : 0;                  // tap row for output k   (gy = 2*oy0-1+q is odd iff q is even)
-        const int tyA = tyB + 2;                          // tap row for output k-1
-        if (gy >= 0 && gy < H) {
+    for (int r = 0; r < 2 * RS + 4; ++r) {
+        const int iy = iy_first + r;
+        u64 v[6];
 #pragma unroll
-            for (int tx = 0; tx < 4; ++tx) {
-                const int gx = 2 * ox - 1 + tx;
-                if (gx < 0 || gx >= W) continue;
-                u64 d = bv;
+        for (int j = 0; j < 6; ++j) v[j] = vn[j];
+        if (r + 1 < 2 * RS + 4) fetch_row(r + 1);
+        // scatter this input row into the three depthwise rows it feeds: ky = 2 -> row iy-1 (slot (r+1)%3, completes),
+        // ky = 1 -> row iy (slot (r+2)%3), ky = 0 -> row iy+1 (slot r%3, starts from the bias)
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+        for (int tx = 0; tx < 4; ++tx) {
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) d = ffma2(wv[ky * 3 + kx], r[(q + ky) % 3][tx + kx], d);
-                d = lrelu_agc2(d);
-                accB = ffma2(ldg2(fir16 + (tyB * 4 + tx) * C + c), d, accB);
-                accA = ffma2(ldg2(fir16 + (tyA * 4 + tx) * C + c), d, accA);
+            for (int kx = 0; kx < 3; ++kx) {
+                dw[(r + 1) % 3][tx] = ffma2(wv[6 + kx], v[tx + kx], dw[(r + 1) % 3][tx]);
+                dw[(r + 2) % 3][tx] = ffma2(wv[3 + kx], v[tx + kx], dw[(r + 2) % 3][tx]);
+                dw[r % 3][tx] = ffma2(wv[kx], v[tx + kx], dw[r % 3][tx]);
             }
         }
-        if ((q & 1) && q >= 3) {                          // gy = 2k even: last contribution (tap 3) to output row k-1 of this strip
-            const size_t o = ((img * H2 + (k - 1)) * W2 + ox) * (size_t)C + c;
-            const float2 v = unpk2(accA);
-            if (out_f32) *reinterpret_cast<float2*>(out_f32 + o) = v;
-            if (out_hi) {
-                __half h0, l0, h1, l1;
-                split_f16(v.x, kActSplitScale, h0, l0);
-                split_f16(v.y, kActSplitScale, h1, l1);
-                *reinterpret_cast<__half2*>(out_hi + o) = __halves2half2(h0, h1);
-                *reinterpret_cast<__half2*>(out_lo + o) = __halves2half2(l0, l1);
+        if (r >= 2) {                                     // depthwise row gy = iy - 1 is complete
+            const int q = r - 2;                          // gy = 2*oy0 - 1 + q
+            const int gy = iy - 1;
+            const int tyB = (q & 1) ? 1 : 0, tyA = tyB + 2;
+            if (gy >= 0 && gy < H) {
+#pragma unroll
+                for (int tx = 0; tx < 4; ++tx) {
+                    if (!dwok[tx]) continue;
+                    const u64 d = lrelu_agc2(dw[(r + 1) % 3][tx]);
+                    accB = ffma2(firp[(tyB * 4 + tx) * fstride], d, accB);
+                    accA = ffma2(firp[(tyA * 4 + tx) * fstride], d, accA);
+                }
             }
+            if ((q & 1) && q >= 3) {                      // gy = 2k even: last tap of output row k-1 = oy0 + (q-3)/2
+                const int orow = oy0 + ((q - 3) >> 1);
+                const size_t o = ((img * H2 + orow) * W2 + ox) * (size_t)C + c;
+                const float2 ov = unpk2(accA);
+                if (out_f32) *reinterpret_cast<float2*>(out_f32 + o) = ov;
+                if (out_hi) {
+                    __half h0, l0, h1, l1;
+                    split_f16(ov.x, kActSplitScale, h0, l0);
+                    split_f16(ov.y, kActSplitScale, h1, l1);
+                    *reinterpret_cast<__half2*>(out_hi + o) = __halves2half2(h0, h1);
+                    *reinterpret_cast<__half2*>(out_lo + o) = __halves2half2(l0, l1);
+                }
+            }
+            if (q & 1) { accA = accB; accB = 0ull; }
         }
-        if (q & 1) { accA = accB; accB = 0ull; }          // row k becomes "k-1" for the next pair of depthwise rows
+#pragma unroll
+        for (int tx = 0; tx < 4; ++tx) dw[(r + 1) % 3][tx] = bv;   // slot is reused by depthwise row iy + 2
     }
 }
 
@@ -237,7 +332,7 @@ cudaError_t launch_dw3x3_down(const float* in, const float* w9, const float* bia
         const uint32_t items = (uint32_t)(per_img * cnt);
         const size_t oi = (size_t)i0 * H * W * C, oo = (size_t)i0 * H2 * W2 * C;
         auto kern = (rs == 8) ? dw3x3_down_kernel<8> : dw3x3_down_kernel<4>;
-        kern<<<(items + 255) / 256, 256, 0, s>>>(in + oi, w9, bias, fir16, out_f32 ? out_f32 + oo : nullptr,
+        kern<<<(items + 255) / 256, 256, 16 * C * sizeof(float), s>>>(in + oi, w9, bias, fir16, out_f32 ? out_f32 + oo : nullptr,
                                                 out_hi ? out_hi + oo : nullptr, out_lo ? out_lo + oo : nullptr,
                                                 items, host_log2(W2), host_log2(H2), host_log2(C / 2), host_log2(strips));
     });

@@ -17,7 +17,8 @@ cudaError_t configure_sepconv_tc();
 cudaError_t launch_stem(const float* x_nchw, const float* w, const float* b, float* out,
                         int n, int H, int W, int C0, cudaStream_t s);
 // depthwise 3x3 (pad 1) + bias + lrelu_agc, NHWC -> NHWC.  w9 is tap-major [9][C].
-cudaError_t launch_dw3x3(const float* in, const float* w9, const float* bias, float* out,
+// Writes fp32 (out, if non-null) and/or the scaled fp16 hi/lo split (out_hi/out_lo, if non-null).
+cudaError_t launch_dw3x3(const float* in, const float* w9, const float* bias, float* out, __half* out_hi, __half* out_lo,
                          int n, int H, int W, int C, cudaStream_t s);
 // depthwise 3x3 + bias + lrelu_agc, then 4x4 FIR stride 2 pad 1 (taps fir16 [16][C]).
 // Writes fp32 [n,H/2,W/2,C] to out_f32 (if non-null) and/or the scaled fp16 hi/lo split

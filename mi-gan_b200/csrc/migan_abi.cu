@@ -537,6 +537,7 @@ struct PlanBuilder {
         const bool tc = (path != MIGAN_PATH_SIMT);
         const float* gemm_in = nullptr;
         __half *ghi = nullptr, *glo = nullptr;
+        bool presplit = L.down;
         if (L.down) {
             Step s; s.kind = K_DWDOWN; s.L = &L; s.in = in; s.n = n; s.H = L.res_in; s.W = L.res_in; s.C = L.cin;
             if (tc) {
@@ -553,6 +554,15 @@ struct PlanBuilder {
             set_tap(s, L.p + "dw_act", S[t1], L.cin, L.res_in, L.res_in);
             steps.push_back(s);
             gemm_in = S[t1];
+        } else if (L.cout >= 512 && !rgb) {
+            // Cout spans 4 CTA N tiles: a fused prologue would re-run the depthwise stage 4x, so run it once as its
+            // own kernel and hand the GEMM a pre-split operand (these layers are small: res <= 64)
+            Step s; s.kind = K_DW; s.L = &L; s.in = in; s.n = n; s.H = L.res_in; s.W = L.res_in; s.C = L.cin;
+            s.hi = reinterpret_cast<__half*>(S[t1]);
+            s.lo = s.hi + (size_t)n * L.res_in * L.res_in * L.cin;
+            ghi = s.hi; glo = s.lo;
+            steps.push_back(s);
+            presplit = true;
         }
         // 1x1 conv at res_pw
         float* pw_out;
@@ -567,7 +577,7 @@ struct PlanBuilder {
             s.aux = (!raw && L.noise) ? L.noise_dev : nullptr;
             if (tc) {
                 s.kind = K_SEPCONV_TC;
-                s.in = L.down ? nullptr : in;  // down: A operand comes pre-split from K_DWDOWN
+                s.in = presplit ? nullptr : in;  // pre-split A operand from K_DWDOWN / K_DW
                 s.hi = ghi; s.lo = glo;
                 const char* err = migan::sepconv_tc_plan(&s.tc, path == MIGAN_PATH_TC_FAST ? 1 : 3, s.in, ghi, glo, L.w9_tc, L.bias_tc,
                                                          L.pw_hi, L.pw_lo, L.tc_inv_scale, s.aux, pw_out, n, L.res_pw, L.cin, L.cout, s.act, rgb);
@@ -719,7 +729,7 @@ int run_step(migan_ctx* ctx, const Step& s, const float* x, float* y, cudaStream
             e = migan::launch_stem(in, ctx->fromrgb_w, ctx->fromrgb_b, out, s.n, s.H, s.W, s.C, st);
             break;
         case K_DW:
-            e = migan::launch_dw3x3(in, s.L->w9, s.L->bias, out, s.n, s.H, s.W, s.C, st);
+            e = migan::launch_dw3x3(in, s.L->w9, s.L->bias, s.out, s.hi, s.lo, s.n, s.H, s.W, s.C, st);
             break;
         case K_DWDOWN:
             e = migan::launch_dw3x3_down(in, s.L->w9, s.L->bias, s.L->fir16, s.out, s.hi, s.lo, s.n, s.H, s.W, s.C, st);
