@@ -72,6 +72,7 @@ struct Params {
     uint32_t in_chunk_bytes;                  // tile_n*(tile_h+2)*(tile_w+2)*128
     uint32_t in_stage_stride;                 // rounded to 1024
     uint32_t off_in, off_a, off_b, off_epi;   // smem offsets from the 1024-aligned base
+    uint32_t off_dw;                          // [10][cin] depthwise taps + bias staged in smem (0xFFFFFFFF: read from global)
     int ablate;                               // debug: bitmask of pipeline stages to skip (timing experiments only)
     int prefetch;                             // L2 prefetch distance of the producer, in chunks / K-blocks
     // fused torgb + image path (SynthesisBlock.forward, migan_inference.py:308-313); needs num_n_tiles == 1
@@ -99,14 +100,30 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifndef MIGAN_TC_WAIT_MODE
+#define MIGAN_TC_WAIT_MODE 1   // 0: try_wait with a long suspend hint, 1: try_wait (default time limit), 2: test_wait spin
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    // suspend-time hint: let the hardware park the warp instead of burning issue slots on polling
+#if MIGAN_TC_WAIT_MODE == 0
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+#elif MIGAN_TC_WAIT_MODE == 1
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 // Bounded wait: a protocol bug must never hang the GPU -- report and trap instead.
@@ -119,7 +136,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int cod
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) mbar_timeout(code, parity, error_flag);
+        if (++spins > (1u << 26)) mbar_timeout(code, parity, error_flag);
     }
 }
 
@@ -261,30 +278,41 @@ __device__ __forceinline__ void prologue_chunk(const float4* __restrict__ sin, u
         const int cg = cg0 + cvec * 4;
         F4 w[9];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) w[t] = as_f4(ldg4(w9 + t * cin + cg));
-        const F4 bv = as_f4(ldg4(bias + cg));
+        for (int t = 0; t < 9; ++t) w[t] = as_f4(*reinterpret_cast<const float4*>(w9 + t * cin + cg));
+        const F4 bv = as_f4(*reinterpret_cast<const float4*>(bias + cg));
         const float4* base = sin + (img_l * (TH + 2) * (TW + 2) + x) * 8 + cvec;
-        F4 r0[3], r1[3], r2[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) { r0[d] = as_f4(base[d * 8]); r1[d] = as_f4(base[ROW_F4 + d * 8]); }
         const uint32_t jchunk = (uint32_t)(g * 4 + (cvec >> 1));
         const uint32_t sub = (uint32_t)(cvec & 1) * 8;
+        // Two output rows per step: four independent accumulation chains (a single row gives only two, and the
+        // FFMA2 dependency latency then dominated the prologue), and the loads of both rows are issued up front.
+        F4 r0[3], r1[3], r2[3], r3[3];
 #pragma unroll
-        for (int y = 0; y < TH; ++y) {
+        for (int d = 0; d < 3; ++d) { r0[d] = as_f4(base[d * 8]); r1[d] = as_f4(base[ROW_F4 + d * 8]); }
 #pragma unroll
-            for (int d = 0; d < 3; ++d) r2[d] = as_f4(base[(y + 2) * ROW_F4 + d * 8]);
-            F4 a = bv;
+        for (int y = 0; y < TH; y += 2) {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) { fma4p(a, w[d], r0[d]); fma4p(a, w[3 + d], r1[d]); fma4p(a, w[6 + d], r2[d]); }
-            uint2 hi, lo;
-            split_pack2(act_scaled2(a.lo), hi.x, lo.x);
-            split_pack2(act_scaled2(a.hi), hi.y, lo.y);
-            const int m = (img_l * TH + y) * TW + x;       // row of the M tile
-            const uint32_t off = (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u + ((jchunk ^ (uint32_t)(m & 7)) << 4) + sub;
-            *reinterpret_cast<uint2*>(a_hi + off) = hi;
-            *reinterpret_cast<uint2*>(a_lo + off) = lo;
+            for (int d = 0; d < 3; ++d) { r2[d] = as_f4(base[(y + 2) * ROW_F4 + d * 8]); r3[d] = as_f4(base[(y + 3) * ROW_F4 + d * 8]); }
+            F4 a = bv, b = bv;
 #pragma unroll
-            for (int d = 0; d < 3; ++d) { r0[d] = r1[d]; r1[d] = r2[d]; }
+            for (int d = 0; d < 3; ++d) {
+                fma4p(a, w[d], r0[d]);     fma4p(b, w[d], r1[d]);
+                fma4p(a, w[3 + d], r1[d]); fma4p(b, w[3 + d], r2[d]);
+                fma4p(a, w[6 + d], r2[d]); fma4p(b, w[6 + d], r3[d]);
+            }
+            uint2 hi0, lo0, hi1, lo1;
+            split_pack2(act_scaled2(a.lo), hi0.x, lo0.x);
+            split_pack2(act_scaled2(b.lo), hi1.x, lo1.x);
+            split_pack2(act_scaled2(a.hi), hi0.y, lo0.y);
+            split_pack2(act_scaled2(b.hi), hi1.y, lo1.y);
+            const int m0 = (img_l * TH + y) * TW + x, m1 = m0 + TW;      // rows of the M tile
+            const uint32_t off0 = (uint32_t)(m0 >> 3) * 1024u + (uint32_t)(m0 & 7) * 128u + ((jchunk ^ (uint32_t)(m0 & 7)) << 4) + sub;
+            const uint32_t off1 = (uint32_t)(m1 >> 3) * 1024u + (uint32_t)(m1 & 7) * 128u + ((jchunk ^ (uint32_t)(m1 & 7)) << 4) + sub;
+            *reinterpret_cast<uint2*>(a_hi + off0) = hi0;
+            *reinterpret_cast<uint2*>(a_lo + off0) = lo0;
+            *reinterpret_cast<uint2*>(a_hi + off1) = hi1;
+            *reinterpret_cast<uint2*>(a_lo + off1) = lo1;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { r0[d] = r2[d]; r1[d] = r3[d]; }
         }
     }
 }
@@ -360,6 +388,11 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
         for (int i = threadIdx.x; i < 3 * p.cout; i += kThreads) s_rgb[i] = __ldg(p.rgb_w + i);
         if (threadIdx.x < 3) s_rgb[3 * 128 + threadIdx.x] = __ldg(p.rgb_b + threadIdx.x);
         if (threadIdx.x < 48 && p.img_lo) s_rgb[3 * 128 + 4 + threadIdx.x] = __ldg(p.rgb_fir + threadIdx.x);
+    }
+    if (a_dw && p.off_dw != 0xFFFFFFFFu) {   // depthwise taps + bias for all channels: read per chunk by every prologue thread
+        float* sdw = reinterpret_cast<float*>(smem_gen + p.off_dw);
+        for (int i = threadIdx.x; i < 9 * p.cin; i += kThreads) sdw[i] = __ldg(p.w9 + i);
+        for (int i = threadIdx.x; i < p.cin; i += kThreads) sdw[9 * p.cin + i] = __ldg(p.bias + i);
     }
     if (warp == kMmaWarp) {  // TMEM: all 512 columns (one CTA per SM by construction)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
@@ -657,10 +690,12 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                 uint8_t* a_hi = smem_gen + p.off_a + sa * kAStage;
                 uint8_t* a_lo = a_hi + kABytes;
                 const int cg0 = kb * kKBlock + g * kChunkC;
+                const float* w9p = (p.off_dw != 0xFFFFFFFFu) ? reinterpret_cast<const float*>(smem_gen + p.off_dw) : p.w9;
+                const float* bp = (p.off_dw != 0xFFFFFFFFu) ? w9p + 9 * p.cin : p.bias;
                 if (p.ablate & 1) {}
-                else if (p.tile_w == 16) prologue_chunk<1, 8, 16>(sin, a_hi, a_lo, p.w9, p.bias, p.cin, cg0, g, tg);
-                else if (p.tile_w == 8) prologue_chunk<2, 8, 8>(sin, a_hi, a_lo, p.w9, p.bias, p.cin, cg0, g, tg);
-                else prologue_chunk<8, 4, 4>(sin, a_hi, a_lo, p.w9, p.bias, p.cin, cg0, g, tg);
+                else if (p.tile_w == 16) prologue_chunk<1, 8, 16>(sin, a_hi, a_lo, w9p, bp, p.cin, cg0, g, tg);
+                else if (p.tile_w == 8) prologue_chunk<2, 8, 8>(sin, a_hi, a_lo, w9p, bp, p.cin, cg0, g, tg);
+                else prologue_chunk<8, 4, 4>(sin, a_hi, a_lo, w9p, bp, p.cin, cg0, g, tg);
                 if (tr) TC_TRACE(3, it, 3);
                 fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 __syncwarp();
@@ -805,7 +840,12 @@ const char* sepconv_tc_plan(SepconvTcArgs* args, int passes, const float* in_f32
     p.off_a = p.in_stages * p.in_stage_stride;
     p.off_b = p.off_a + p.a_stages * kAStage;
     p.off_epi = p.off_b + p.b_stages * b_stage;
-    const uint32_t smem_bytes = p.off_epi + epi + 1024;
+    uint32_t smem_bytes = p.off_epi + epi + 1024;
+    p.off_dw = 0xFFFFFFFFu;
+    if (p.a_mode == 0 && smem_bytes + 40u * cin <= kSmemLimit - 4096) {   // taps + bias table if it fits
+        p.off_dw = p.off_epi + epi;
+        smem_bytes += 40u * cin;
+    }
     if (smem_bytes > kSmemLimit - 4096) return "shared memory budget exceeded (layout)";
     p.error_flag = g_error_flag;
     p.prefetch = (p.a_mode == 0) ? 4 : 2;

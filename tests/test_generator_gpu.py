@@ -166,6 +166,17 @@ def test_forward_host_end_to_end(cuda_device):
     assert errs(y, O.generator_forward(sd, x, R))[0] < TOL_MAX_ABS
 
 
+def test_forward_host_micro_batch_pipeline(cuda_device):
+    """n = 16 takes the 2-micro-batch H2D / compute / D2H pipeline; results must equal the resident-input path."""
+    R, N = 64, 16
+    g, sd = make_model(R, "tc")
+    x = O.make_input(R, N, seed=6).pin_memory()
+    y = g.forward_host(x)
+    want = g(x.to(cuda_device)).cpu()
+    assert torch.equal(y, want)
+    assert errs(y[[0, 15]], O.generator_forward(sd, x[[0, 15]], R))[0] < TOL_MAX_ABS
+
+
 def test_from_img_mask(cuda_device):
     R = 64
     g, sd = make_model(R, "simt")
