@@ -342,54 +342,67 @@ cudaError_t launch_dw3x3_down(const float* in, const float* w9, const float* bia
 // 2x FIR up-sampling (polyphase: only the taps that meet a non-zero of the zero-inserted
 // signal) + noise + act + skip.  out[o] = sum_t f[t] * z[o + t - 2], z[2i] = x[i], z[odd] = 0.
 // --------------------------------------------------------------------------------------
+// Thread = (low-res pixel, 4 channels) -> its 2x2 output pixels: 9 neighbour loads feed 4 outputs (instead of
+// 4 loads per output) and the 16 per-channel taps come from a shared-memory table (instead of 4 global loads per output).
 __global__ void __launch_bounds__(256)
 up2_noise_act_skip_kernel(const float* __restrict__ t, const float* __restrict__ fir16,
                           const float* __restrict__ noise, const float* __restrict__ skip,
                           float* __restrict__ out, uint32_t items, int lw, int lh, int lcv) {
+    extern __shared__ float4 s_taps[];                    // [16][C/4]
+    const int w = 1 << lw, h = 1 << lh, W2 = 2 * w, C = 4 << lcv, CV = 1 << lcv;
+    for (int i = threadIdx.x; i < 16 * CV; i += 256) s_taps[i] = ldg4(fir16 + i * 4);
+    __syncthreads();
     const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
     if (idx >= items) return;
-    const int w = 1 << lw, h = 1 << lh, W2 = 2 * w, H2 = 2 * h, C = 4 << lcv;
-    const int c = (int)(idx & ((1u << lcv) - 1)) * 4;
-    const uint32_t p = idx >> lcv;
-    const int ox = (int)(p & (W2 - 1));
-    const int oy = (int)((p >> (lw + 1)) & (H2 - 1));
-    const size_t img = p >> (lw + lh + 2);
-    const float* src = t + img * (size_t)h * w * C + c;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int cv = (int)(idx & (CV - 1));
+    const uint32_t p = idx >> lcv;                        // low-res pixel index over the image group
+    const int ix = (int)(p & (w - 1));
+    const int iy = (int)((p >> lw) & (h - 1));
+    const size_t img = p >> (lw + lh);
+    const float* src = t + img * (size_t)h * w * C + cv * 4;
+    float4 nb[3][3];
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const int ty = (oy & 1) + 2 * a;
-        const int iy = (oy + ty - 2) >> 1;
-        if (iy < 0 || iy >= h) continue;
+    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-        for (int bb = 0; bb < 2; ++bb) {
-            const int tx = (ox & 1) + 2 * bb;
-            const int ix = (ox + tx - 2) >> 1;
-            if (ix < 0 || ix >= w) continue;
-            fma4(acc, ldg4(fir16 + (ty * 4 + tx) * C + c), ldg4(src + ((size_t)iy * w + ix) * C));
+        for (int dx = 0; dx < 3; ++dx) {
+            const int yy = iy + dy - 1, xx = ix + dx - 1;
+            nb[dy][dx] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? ldg4(src + ((size_t)yy * w + xx) * C)
+                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    }
-    if (noise) {
-        const float nz = __ldg(noise + oy * W2 + ox);
-        acc.x += nz; acc.y += nz; acc.z += nz; acc.w += nz;
-    }
-    acc = lrelu_agc4(acc);
-    const size_t o = (size_t)p * C + c;
-    if (skip) {
-        const float4 sk = ldg4(skip + o);
-        acc.x += sk.x; acc.y += sk.y; acc.z += sk.z; acc.w += sk.w;
-    }
-    stg4(out + o, acc);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            // output (2iy+a, 2ix+b): taps ty = a, a+2 meet rows iy-1+a, iy+a ; tx = b, b+2 meet cols ix-1+b, ix+b
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int v = 0; v < 2; ++v)
+                    fma4(acc, s_taps[((a + 2 * u) * 4 + (b + 2 * v)) * CV + cv], nb[a + u][b + v]);
+            const int oy = 2 * iy + a, ox = 2 * ix + b;
+            if (noise) {
+                const float nz = __ldg(noise + oy * W2 + ox);
+                acc.x += nz; acc.y += nz; acc.z += nz; acc.w += nz;
+            }
+            acc = lrelu_agc4(acc);
+            const size_t o = ((img * (size_t)(2 * h) + oy) * W2 + ox) * C + cv * 4;
+            if (skip) {
+                const float4 sk = ldg4(skip + o);
+                acc.x += sk.x; acc.y += sk.y; acc.z += sk.z; acc.w += sk.w;
+            }
+            stg4(out + o, acc);
+        }
 }
 
 cudaError_t launch_up2(const float* t, const float* fir16, const float* noise, const float* skip,
                        float* out, int n, int h, int w, int C, cudaStream_t s) {
-    const size_t per_img = (size_t)4 * h * w * (C / 4);
+    const size_t per_img = (size_t)h * w * (C / 4);
     return for_image_groups(n, per_img, [&](int i0, int cnt) {
         const uint32_t items = (uint32_t)(per_img * cnt);
         const size_t oi = (size_t)i0 * h * w * C, oo = (size_t)i0 * 4 * h * w * C;
-        up2_noise_act_skip_kernel<<<(items + 255) / 256, 256, 0, s>>>(t + oi, fir16, noise, skip ? skip + oo : nullptr, out + oo,
-                                                                     items, host_log2(w), host_log2(h), host_log2(C / 4));
+        up2_noise_act_skip_kernel<<<(items + 255) / 256, 256, 16 * C * sizeof(float), s>>>(
+            t + oi, fir16, noise, skip ? skip + oo : nullptr, out + oo, items, host_log2(w), host_log2(h), host_log2(C / 4));
     });
 }
 

@@ -136,7 +136,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int cod
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) mbar_timeout(code, parity, error_flag);
+        if (++spins > (1u << 22)) mbar_timeout(code, parity, error_flag);
     }
 }
 
