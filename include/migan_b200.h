@@ -71,12 +71,19 @@ size_t migan_workspace_bytes(const migan_ctx* ctx, int n);
 int migan_forward(migan_ctx* ctx, const float* x, float* y, int n,
                   void* workspace, size_t workspace_bytes, int path, void* stream);
 
-/* Same with HOST x / y (pinned for full speed): H2D copy, forward, D2H copy, stream
- * synchronize.  The device staging buffers live at the end of the workspace:
+/* Same with HOST x / y (pinned for full speed): H2D copy, forward, D2H copy; y_host is complete on return.
+ * The batch is split into two micro-batches whose copies overlap the kernels (three streams).  The device
+ * staging buffers (two slots) live at the end of the workspace:
  * workspace_bytes must be >= migan_workspace_bytes(n) + migan_host_staging_bytes(n). */
 size_t migan_host_staging_bytes(const migan_ctx* ctx, int n);
 int migan_forward_host(migan_ctx* ctx, const float* x_host, float* y_host, int n,
                        void* workspace, size_t workspace_bytes, int path, void* stream);
+/* Serving form: enqueue only.  Consecutive calls alternate between the two staging slots, so the copies of
+ * batch t+1 overlap the kernels and the copy-out of batch t; migan_host_wait() blocks until every enqueued
+ * batch has landed in its y_host.  x_host / y_host must stay valid (and unmodified) until then. */
+int migan_forward_host_async(migan_ctx* ctx, const float* x_host, float* y_host, int n,
+                             void* workspace, size_t workspace_bytes, int path, void* stream);
+int migan_host_wait(migan_ctx* ctx);
 
 /* Kernels launched by the most recent migan_forward on this context. */
 int migan_last_launch_count(const migan_ctx* ctx);

@@ -26,6 +26,8 @@ SYMBOLS = [
     ("migan_forward", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     ("migan_host_staging_bytes", c_size_t, [c_void_p, c_int]),
     ("migan_forward_host", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    ("migan_forward_host_async", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    ("migan_host_wait", c_int, [c_void_p]),
     ("migan_last_launch_count", c_int, [c_void_p]),
     ("migan_set_profiling", c_int, [c_void_p, c_int]),
     ("migan_profile_num_steps", c_int, [c_void_p]),

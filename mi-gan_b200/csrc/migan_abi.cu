@@ -158,6 +158,9 @@ struct migan_ctx {
     // host-buffer pipeline (migan_forward_host): copy streams + events, created on first use
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> host_events;
+    cudaEvent_t slot_compute_done[2] = {nullptr, nullptr}, slot_out_done[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
+    unsigned host_calls = 0;
     int tap_cache_path = -1;          // tap enumeration cache (migan_tap_info)
     std::vector<std::pair<std::string, std::array<int, 3>>> tap_cache;
 };
@@ -300,6 +303,10 @@ int migan_destroy(migan_ctx* ctx) {
     if (!ctx) return MIGAN_OK;
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->host_events) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->slot_compute_done[i]) cudaEventDestroy(ctx->slot_compute_done[i]);
+        if (ctx->slot_out_done[i]) cudaEventDestroy(ctx->slot_out_done[i]);
+    }
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->arena && ctx->device >= 0) {
@@ -510,7 +517,7 @@ size_t migan_workspace_bytes(const migan_ctx* ctx, int n) {
 size_t migan_host_staging_bytes(const migan_ctx* ctx, int n) {
     if (!ctx || n <= 0) return 0;
     const size_t px = (size_t)n * ctx->resolution * ctx->resolution * sizeof(float);
-    return align_up(4 * px, 1024) + align_up(3 * px, 1024);
+    return 2 * (align_up(4 * px, 1024) + align_up(3 * px, 1024));   // two slots: consecutive calls overlap
 }
 
 }  // extern "C"
@@ -841,8 +848,11 @@ int migan_profile_step(migan_ctx* ctx, int index, const char** label, float* ms,
     return MIGAN_OK;
 }
 
-int migan_forward_host(migan_ctx* ctx, const float* x_host, float* y_host, int n, void* workspace,
-                       size_t workspace_bytes, int path, void* stream) {
+// Enqueue H2D -> forward -> D2H for one host batch without waiting for it.  Two staging slots alternate, so the
+// copies of call c+1 overlap the kernels / copy-out of call c (a serving loop submits batches back to back and
+// collects them with migan_host_wait).  Within a call the batch is split into micro-batches for the same reason.
+static int forward_host_enqueue(migan_ctx* ctx, const float* x_host, float* y_host, int n, void* workspace,
+                                size_t workspace_bytes, int path, void* stream, int* slot_out) {
     if (!ctx || !x_host || !y_host || !workspace) return fail(MIGAN_ERR_INVALID, "null argument");
     if (n <= 0) return fail(MIGAN_ERR_INVALID, "batch size must be positive, got %d", n);
     const size_t ws = migan_workspace_bytes(ctx, n);
@@ -850,8 +860,11 @@ int migan_forward_host(migan_ctx* ctx, const float* x_host, float* y_host, int n
         return fail(MIGAN_ERR_WORKSPACE, "workspace too small for host staging: %zu < %zu bytes", workspace_bytes,
                     ws + migan_host_staging_bytes(ctx, n));
     const size_t px = (size_t)n * ctx->resolution * ctx->resolution * sizeof(float);
-    float* xd = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + ws);
-    float* yd = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + ws + align_up(4 * px, 1024));
+    const size_t slot_bytes = align_up(4 * px, 1024) + align_up(3 * px, 1024);
+    const int slot = (int)(ctx->host_calls++ & 1);
+    unsigned char* sbase = static_cast<unsigned char*>(workspace) + ws + slot * slot_bytes;
+    float* xd = reinterpret_cast<float*>(sbase);
+    float* yd = reinterpret_cast<float*>(sbase + align_up(4 * px, 1024));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaSetDevice(ctx->device));
     // Micro-batch pipeline: H2D of micro-batch k+1 and D2H of k-1 overlap the kernels of k (three streams).
@@ -864,36 +877,68 @@ int migan_forward_host(migan_ctx* ctx, const float* x_host, float* y_host, int n
     if (!ctx->s_in) {
         CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot_compute_done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot_out_done[i], cudaEventDisableTiming));
+        }
     }
-    while ((int)ctx->host_events.size() < 2 * M + 2) {
+    while ((int)ctx->host_events.size() < 2 * (2 * M + 1)) {
         cudaEvent_t e;
         CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->host_events.push_back(e);
     }
-    cudaEvent_t ev_start = ctx->host_events[2 * M], ev_done = ctx->host_events[2 * M + 1];
+    cudaEvent_t* ev = ctx->host_events.data() + slot * (2 * M + 1);   // per-slot events: [in_k, c_k] x M, start
+    cudaEvent_t ev_start = ev[2 * M];
     const int m = n / M;
     const size_t xs = (size_t)m * 4 * ctx->resolution * ctx->resolution, ys = (size_t)m * 3 * ctx->resolution * ctx->resolution;
     CUDA_TRY(cudaEventRecord(ev_start, st));                  // order after whatever the caller queued on `stream`
     CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ev_start, 0));
     CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ev_start, 0));
+    if (ctx->slot_used[slot]) {
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->slot_compute_done[slot], 0));   // xd[slot] free again
+        CUDA_TRY(cudaStreamWaitEvent(st, ctx->slot_out_done[slot], 0));              // yd[slot] copied out
+    }
     for (int k = 0; k < M; ++k) {
         CUDA_TRY(cudaMemcpyAsync(xd + k * xs, x_host + k * xs, xs * sizeof(float), cudaMemcpyHostToDevice, ctx->s_in));
-        CUDA_TRY(cudaEventRecord(ctx->host_events[2 * k], ctx->s_in));
+        CUDA_TRY(cudaEventRecord(ev[2 * k], ctx->s_in));
     }
     int launches = 0;
     for (int k = 0; k < M; ++k) {
-        CUDA_TRY(cudaStreamWaitEvent(st, ctx->host_events[2 * k], 0));
+        CUDA_TRY(cudaStreamWaitEvent(st, ev[2 * k], 0));
         int rc = migan_forward(ctx, xd + k * xs, yd + k * ys, m, workspace, ws, path, stream);
         if (rc) return rc;
         launches += ctx->last_launches;
-        CUDA_TRY(cudaEventRecord(ctx->host_events[2 * k + 1], st));
-        CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->host_events[2 * k + 1], 0));
+        CUDA_TRY(cudaEventRecord(ev[2 * k + 1], st));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ev[2 * k + 1], 0));
         CUDA_TRY(cudaMemcpyAsync(y_host + k * ys, yd + k * ys, ys * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_out));
     }
     ctx->last_launches = launches;
-    CUDA_TRY(cudaEventRecord(ev_done, ctx->s_out));
-    CUDA_TRY(cudaStreamWaitEvent(st, ev_done, 0));            // later work on `stream` sees the finished copies
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventRecord(ctx->slot_compute_done[slot], st));
+    CUDA_TRY(cudaEventRecord(ctx->slot_out_done[slot], ctx->s_out));
+    ctx->slot_used[slot] = true;
+    if (slot_out) *slot_out = slot;
+    return MIGAN_OK;
+}
+
+int migan_forward_host(migan_ctx* ctx, const float* x_host, float* y_host, int n, void* workspace,
+                       size_t workspace_bytes, int path, void* stream) {
+    int slot = 0;
+    int rc = forward_host_enqueue(ctx, x_host, y_host, n, workspace, workspace_bytes, path, stream, &slot);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventSynchronize(ctx->slot_out_done[slot]));   // y_host is complete on return
+    return MIGAN_OK;
+}
+
+int migan_forward_host_async(migan_ctx* ctx, const float* x_host, float* y_host, int n, void* workspace,
+                             size_t workspace_bytes, int path, void* stream) {
+    return forward_host_enqueue(ctx, x_host, y_host, n, workspace, workspace_bytes, path, stream, nullptr);
+}
+
+int migan_host_wait(migan_ctx* ctx) {
+    if (!ctx) return fail(MIGAN_ERR_INVALID, "null ctx");
+    if (!ctx->s_out) return MIGAN_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
     return MIGAN_OK;
 }
 

@@ -191,9 +191,10 @@ class Generator(nn.Module):
         return y
 
     @torch.no_grad()
-    def forward_host(self, x_host: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward_host(self, x_host: torch.Tensor, out: Optional[torch.Tensor] = None, wait: bool = True) -> torch.Tensor:
         """End-to-end call with HOST tensors (pinned for full speed): H2D, forward, D2H, sync --
-        what scripts/demo.py:131-136 does around the reference model."""
+        what scripts/demo.py:131-136 does around the reference model.  With wait=False the call only
+        enqueues (serving loop: submit batches back to back, then `host_wait()`); `out` is valid after the wait."""
         r = self.resolution
         if x_host.is_cuda or x_host.dtype != torch.float32 or x_host.dim() != 4 or tuple(x_host.shape[1:]) != (4, r, r):
             raise RuntimeError("forward_host expects a CPU float32 tensor of shape [N, 4, %d, %d]" % (r, r))
@@ -208,9 +209,14 @@ class Generator(nn.Module):
             eng = self._engine(device)
             ws = eng.workspace(n, host_staging=True)
             stream = torch.cuda.current_stream(device).cuda_stream
-            _abi.check(eng.lib.migan_forward_host(eng.handle, x_host.data_ptr(), out.data_ptr(), n, ws.data_ptr(),
-                                                  ws.numel(), self._path_id(), stream))
+            fn = eng.lib.migan_forward_host if wait else eng.lib.migan_forward_host_async
+            _abi.check(fn(eng.handle, x_host.data_ptr(), out.data_ptr(), n, ws.data_ptr(), ws.numel(), self._path_id(), stream))
         return out
+
+    def host_wait(self) -> None:
+        """Block until every batch enqueued with forward_host(wait=False) has landed in its output tensor."""
+        for eng in self._engines.values():
+            _abi.check(eng.lib.migan_host_wait(eng.handle))
 
     def from_img_mask(self, img: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
         """Convenience stem of the callers (scripts/demo.py:56-66): img in [-1,1], mask 1 = known."""

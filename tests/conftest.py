@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # The CPU oracle runs on oneDNN: on boxes whose CPU quota is far below the visible core count (GPU box:
+    # 128 visible, 16 usable) the default thread count makes it ~25x slower.
+    import torch
+    torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
 
 
 @pytest.fixture(scope="session")

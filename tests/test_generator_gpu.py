@@ -177,6 +177,20 @@ def test_forward_host_micro_batch_pipeline(cuda_device):
     assert errs(y[[0, 15]], O.generator_forward(sd, x[[0, 15]], R))[0] < TOL_MAX_ABS
 
 
+def test_forward_host_async_serving_loop(cuda_device):
+    """Back-to-back submissions alternate staging slots; every output must be complete after host_wait()."""
+    R, N = 64, 8
+    g, sd = make_model(R, "tc")
+    xs = [O.make_input(R, N, seed=40 + i).pin_memory() for i in range(5)]
+    ys = [torch.empty(N, 3, R, R).pin_memory() for _ in range(5)]
+    for x, y in zip(xs, ys):
+        g.forward_host(x, out=y, wait=False)
+    g.host_wait()
+    for x, y in zip(xs, ys):
+        assert torch.equal(y, g(x.to(cuda_device)).cpu())
+    assert errs(ys[3][:2], O.generator_forward(sd, xs[3][:2], R))[0] < TOL_MAX_ABS
+
+
 def test_from_img_mask(cuda_device):
     R = 64
     g, sd = make_model(R, "simt")
