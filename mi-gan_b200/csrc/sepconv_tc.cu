@@ -471,7 +471,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
         }
     } else if (warp == kMmaWarp) {
         // ================================ MMA issuer ==================================
-        const uint32_t idesc = umma_idesc_f16(p.n_tile);
+        const uint32_t idesc = umma_idesc_f16(p.n_tile), idesc2 = umma_idesc_f16(2 * p.n_tile);
         const uint32_t b_stage_bytes = (uint32_t)p.n_tile * kKBlock * 2 * 2;
         Ring ra(p.a_stages), rb(p.b_stages);
         for (int it = 0; it < my_tiles; ++it) {
@@ -499,14 +499,18 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                     const uint32_t a_hi = smem_base + p.off_a + sa * kAStage, a_lo = a_hi + kABytes;
                     const uint32_t b_hi = smem_base + p.off_b + sb * b_stage_bytes, b_lo = b_hi + b_stage_bytes / 2;
                     const uint64_t dah = umma_desc_sw128(a_hi), dal = umma_desc_sw128(a_lo);
-                    const uint64_t dbh = umma_desc_sw128(b_hi), dbl = umma_desc_sw128(b_lo);
+                    const uint64_t dbh = umma_desc_sw128(b_hi);
+                    (void)b_lo;   // Bl sits right behind Bh in shared memory: [Bh ; Bl] is one K-major operand of 2*n_tile rows
 #pragma unroll
                     for (int k = 0; k < ((p.ablate & 4) ? 0 : kKBlock / 16); ++k) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 16 fp16 = 32 bytes along K inside the SW128 row
-                        tc_mma_f16(tmem_d, dah + adv, dbh + adv, idesc, (kb | k) != 0);
                         if (p.passes == 3) {
-                            tc_mma_f16(tmem_c, dal + adv, dbh + adv, idesc, (kb | k) != 0);
-                            tc_mma_f16(tmem_c, dah + adv, dbl + adv, idesc, 1u);
+                            // [main | corr] = Ah * [Bh ; Bl]^T in ONE instruction (N = 2*n_tile): Ah is read from shared
+                            // memory once for both products; then corr += Al * Bh.
+                            tc_mma_f16(tmem_d, dah + adv, dbh + adv, idesc2, (kb | k) != 0);
+                            tc_mma_f16(tmem_c, dal + adv, dbh + adv, idesc, 1u);
+                        } else {
+                            tc_mma_f16(tmem_d, dah + adv, dbh + adv, idesc, (kb | k) != 0);
                         }
                     }
                     tc_commit(empty_a(sa));                       // A slot reusable once these MMAs retire

@@ -191,6 +191,19 @@ def test_forward_host_async_serving_loop(cuda_device):
     assert errs(ys[3][:2], O.generator_forward(sd, xs[3][:2], R))[0] < TOL_MAX_ABS
 
 
+def test_tc_fast_mode_stated_accuracy(cuda_device):
+    """path="tc_fast" = single fp16 tensor-core pass: NOT fp32-faithful (SURVEY F5 predicts ~1e-2 abs at
+    output scale ~10); it must run and stay within its stated, looser bound."""
+    R, N = 256, 2
+    g, sd = make_model(R, "tc_fast")
+    x = O.make_input(R, N, seed=11)
+    want = O.generator_forward(sd, x, R)
+    mx, mean = errs(g(x.to(cuda_device)), want)
+    print("tc_fast R=%d max-abs=%.3e mean-abs=%.3e |y|max=%.2f" % (R, mx, mean, float(want.abs().max())))
+    assert mx < 1e-1 and mean < 1e-2
+    assert mx > 1e-4   # it really is the single-pass path
+
+
 def test_from_img_mask(cuda_device):
     R = 64
     g, sd = make_model(R, "simt")
