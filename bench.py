@@ -202,6 +202,7 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        parallel.configure_overlap()                                # few NCCL channels + SMs left free for them
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -900,7 +900,12 @@ const char* sepconv_tc_plan(SepconvTcArgs* args, int passes, const float* in_f32
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    args->grid = (unsigned)std::min(p.num_tiles, sms);
+    // Persistent grid = one CTA per SM.  When a collective runs concurrently (multi-GPU all-gather on NCCL's stream) its
+    // CTAs occupy a few SMs; a full-width persistent grid would then run its last CTAs as a second wave.  The sharded
+    // path therefore leaves MIGAN_TC_RESERVE_SMS SMs free (set by migan_b200.parallel.configure_overlap).
+    int reserve = 0;
+    if (const char* e = getenv("MIGAN_TC_RESERVE_SMS")) reserve = std::max(0, std::min(atoi(e), sms / 2));
+    args->grid = (unsigned)std::min(p.num_tiles, sms - reserve);
     args->smem_bytes = smem_bytes;
     args->num_tiles = p.num_tiles;
     memcpy(args->params_blob, &p, sizeof(p));

@@ -11,10 +11,23 @@ batch t+1 (in a serving loop the collective is then off the critical path).
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+def configure_overlap(reserve_sms: int = 8, nccl_channels: int = 8) -> None:
+    """Call BEFORE `init_process_group` and before the first forward.  The output all-gather runs concurrently with
+    the next batch's kernels; NCCL's copy kernels use one SM per channel, and the persistent tensor-core kernel uses
+    one CTA per SM -- if they collide, the persistent kernel's last CTAs run as a second wave.  So NCCL is limited to
+    `nccl_channels` channels (enough for 100 MB per rank per ~13 ms step even at 8 ranks) and the persistent grids leave
+    `reserve_sms` SMs free.  Measured on 2 B200s (migan-512, 32 img/GPU): 14.27 ms/step without the reservation,
+    13.32-13.39 ms with 4-8 SMs reserved (12.9 ms on one GPU).  Respects values already present in the environment."""
+    os.environ.setdefault("NCCL_MAX_NCHANNELS", str(nccl_channels))
+    os.environ.setdefault("NCCL_MIN_NCHANNELS", str(nccl_channels))
+    os.environ.setdefault("MIGAN_TC_RESERVE_SMS", str(reserve_sms))
 
 
 def shard_bounds(global_n: int, world_size: int, rank: int) -> Tuple[int, int]:
