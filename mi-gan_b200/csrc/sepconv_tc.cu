@@ -2,25 +2,29 @@
 //
 //   out = epi( PW( act( DW3x3(in) + b ) ) )          lib/model_zoo/migan_inference.py:154-170
 //
-//   DW3x3 + bias + lrelu_agc   CUDA cores, fp32, on a TMA-staged NHWC tile + 1-pixel halo
-//   PW (1x1 conv, Cin -> Cout) tcgen05.mma kind::f16, M=128 pixels x N<=128 channels per CTA,
-//                              accumulators in TMEM.  fp32-faithful mode: both operands are split
-//                              into fp16 (hi, lo) pairs and  Ah*Bh + Al*Bh + Ah*Bl  is accumulated
-//                              in fp32 (3 passes); fast mode: Ah*Bh only.
-//   epi                        TMEM -> registers: * 2^-k, + noise, lrelu_agc -> swizzled smem
-//                              -> TMA store (NHWC fp32)
+//   DW3x3 + bias + lrelu_agc   CUDA cores (packed FFMA2), fp32, on a TMA-staged NHWC tile + 1-pixel halo
+//   PW (1x1 conv, Cin -> Cout) tcgen05.mma kind::f16, M = 128 pixels x N <= 128 channels per CTA, accumulators in
+//                              TMEM.  fp32-faithful mode: both operands are split into fp16 (hi, lo) pairs;
+//                              [main | corr] = Ah * [Bh ; Bl]^T (one N = 2*n_tile instruction), corr += Al * Bh,
+//                              main + corr summed in the epilogue (separate accumulators: the tensor core truncates
+//                              on accumulate).  Fast mode: Ah * Bh only.
+//   epi                        TMEM -> registers: * 2^-k, + noise, lrelu_agc [-> torgb + image] -> swizzled smem
+//                              -> per-warp TMA store (NHWC fp32)
 //
 // One persistent CTA per SM, warp-specialised:
 //   warps 0-7   prologue       depthwise conv -> fp16 hi/lo A operand in UMMA K-major SW128 layout
 //   warps 8-11  epilogue       one TMEM lane quarter each
-//   warp 12     TMA producer   input chunks (32 channels, fp32, halo'd) and weight K-blocks
+//   warp 12     TMA producer   input chunks (32 channels, fp32, halo'd) and weight K-blocks, L2 prefetch
 //   warp 13     MMA issuer     one elected lane issues tcgen05.mma / tcgen05.commit; owns TMEM
 // All hand-offs are mbarrier pipelines (input ring, A ring, B ring, TMEM accumulator ring).
 //
 // Two A-operand sources:
 //   A_DW  (mode 0) prologue as above (plain layers and the 1x1 of up-sampling layers)
-//   A_TMA (mode 1) the operand was already produced as fp16 hi/lo by dw3x3_down_kernel
-//                  (down-sampling layers); TMA loads it straight into the A ring.
+//   A_TMA (mode 1) the operand was already produced as fp16 hi/lo by dw3x3_down_kernel (down-sampling layers) or
+//                  dw3x3_act_kernel (Cout = 512 layers); TMA loads it straight into the A ring.
+//
+// Debug aids (environment, read at plan time): MIGAN_TC_TRACE="res,cin,cout,torgb" records clock64 stamps of CTA 0
+// (tools/tc_trace.py); MIGAN_TC_ABLATE=<mask> skips pipeline stages for timing experiments (results are wrong).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -53,7 +57,6 @@ constexpr int kChunkC = 32;        // channels per input chunk (128 bytes of fp3
 constexpr uint32_t kABytes = kTileM * kKBlock * 2;   // 16 KB per hi or lo
 constexpr uint32_t kAStage = 2 * kABytes;            // hi + lo
 constexpr uint32_t kEpiBuf = kTileM * 32 * 4;        // 16 KB: 128 rows x 32 fp32
-constexpr int kMaxStages = 8;   // input / B ring slots (A ring: <= 4)
 constexpr uint32_t kSmemLimit = 232448;              // 227 KB
 
 struct Params {
@@ -171,9 +174,6 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
