@@ -200,11 +200,13 @@ __device__ __forceinline__ u64 lrelu_agc2(u64 v) {
     return pk2(fminf(fmaxf(m.x, -kActClamp), kActClamp), fminf(fmaxf(m.y, -kActClamp), kActClamp));
 }
 
-// RS = low-res rows per thread (template: the row walk is fully unrolled).  Register plan per thread:
-//   in[6]      the current input row (columns 2ox-2 .. 2ox+3)
-//   dw[3][4]   partial depthwise sums of the three depthwise rows the current input row touches
-//   w[9], fir[16], bias  per-channel-pair constants;   6 column pointers advanced by one row per step
-// so every load is `[pointer]` with no index arithmetic, and each input row is read exactly once.
+// RS = low-res rows per thread (template: the row walk is fully unrolled).  Thread = (channel pair, PAIR of adjacent
+// low-res columns ox0 = 2*oxp, ox0 + 1, strip of RS rows).  Register plan per thread:
+//   v[8]       the current input row (columns 2ox0-2 .. 2ox0+5), fetched one row ahead (software pipelining)
+//   dw[3][6]   partial depthwise sums of the three depthwise rows the current input row touches; the two middle
+//              depthwise columns feed both outputs, so every activated depthwise value is computed exactly once
+//              horizontally (the one-column version evaluated each column in two threads)
+//   w[9], bias per-channel-pair constants; FIR taps from a shared-memory table; 8 column pointers advanced per row
 template <int RS>
 __global__ void __launch_bounds__(256, 2)
 dw3x3_down_kernel(const float* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ bias,
@@ -214,14 +216,13 @@ dw3x3_down_kernel(const float* __restrict__ in, const float* __restrict__ w9, co
     const int W2 = 1 << lw2, H2 = 1 << lh2, W = 2 * W2, H = 2 * H2, C = 2 << lcp;
     const int c = (int)(idx & ((1u << lcp) - 1)) * 2;
     uint32_t t = idx >> lcp;
-    const int ox = (int)(t & (W2 - 1));
-    t >>= lw2;
+    const int ox0 = (int)(t & ((W2 >> 1) - 1)) * 2;
+    t >>= (lw2 - 1);
     const int strip = (int)(t & ((1u << lstrips) - 1));
     const size_t img = t >> lstrips;
     const int oy0 = strip * RS;
 
-    // FIR taps live in shared memory ([16][C], conflict-free 64-bit reads along the channel pairs): keeping them
-    // in registers (32 per thread) capped the kernel at 2 blocks / SM.
+    // FIR taps live in shared memory ([16][C], conflict-free 64-bit reads along the channel pairs)
     extern __shared__ float s_fir[];
     for (int i = threadIdx.x; i < 16 * C; i += 256) s_fir[i] = __ldg(fir16 + i);
     __syncthreads();
@@ -233,37 +234,34 @@ dw3x3_down_kernel(const float* __restrict__ in, const float* __restrict__ w9, co
     for (int k = 0; k < 9; ++k) wv[k] = ldg2(w9 + k * C + c);
     const u64 bv = ldg2(bias + c);
 
-    // column pointers / validity (columns 2ox-2 .. 2ox+3), positioned on input row 2*oy0-2
     const int iy_first = 2 * oy0 - 2;
-    const float* colp[6];
-    bool colok[6];
+    const float* colp[8];
+    bool colok[8];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        const int ix = 2 * ox - 2 + j;
+    for (int j = 0; j < 8; ++j) {
+        const int ix = 2 * ox0 - 2 + j;
         colok[j] = (ix >= 0 && ix < W);
-        colp[j] = in + ((img * H + iy_first) * (size_t)W + (colok[j] ? ix : 0)) * C + c;   // may point before the tensor: only dereferenced when valid
+        colp[j] = in + ((img * H + iy_first) * (size_t)W + (colok[j] ? ix : 0)) * C + c;   // only dereferenced when valid
     }
     const size_t row_stride = (size_t)W * C;
-    bool dwok[4];
+    bool dwok[6];
 #pragma unroll
-    for (int tx = 0; tx < 4; ++tx) dwok[tx] = (2 * ox - 1 + tx >= 0) && (2 * ox - 1 + tx < W);
+    for (int tx = 0; tx < 6; ++tx) dwok[tx] = (2 * ox0 - 1 + tx >= 0) && (2 * ox0 - 1 + tx < W);
 
-    u64 dw[3][4];                                         // dw[s]: partial sums of depthwise row (iy - 1 + s') ...
+    u64 dw[3][6];
 #pragma unroll
     for (int s2 = 0; s2 < 3; ++s2)
 #pragma unroll
-        for (int tx = 0; tx < 4; ++tx) dw[s2][tx] = bv;
-    u64 accA = 0ull, accB = 0ull;                         // FIR accumulators of output rows k-1 and k
+        for (int tx = 0; tx < 6; ++tx) dw[s2][tx] = bv;
+    u64 accA[2] = {0ull, 0ull}, accB[2] = {0ull, 0ull};   // FIR accumulators of output rows k-1 / k, columns ox0 / ox0+1
 
-    // input rows r = 0 .. 2RS+3  (iy = iy_first + r); input row r completes depthwise row gy = iy - 1 (q = r - 2).
-    // The loads of row r+1 are issued before row r is consumed (software pipelining: ncu showed 44 % of the stalls
-    // on the scoreboard of loads used immediately after issue).
-    u64 vn[6];
+    // input rows r = 0 .. 2RS+3 (iy = iy_first + r); input row r completes depthwise row gy = iy - 1 (q = r - 2)
+    u64 vn[8];
     auto fetch_row = [&](int r) {
         const int iy = iy_first + r;
         const bool rowok = (iy >= 0 && iy < H);
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
+        for (int j = 0; j < 8; ++j) {
             vn[j] = (rowok && colok[j]) ? ldg2(colp[j]) : 0ull;
             colp[j] += row_stride;
         }
@@ -272,14 +270,13 @@ dw3x3_down_kernel(const float* __restrict__ in, const float* __restrict__ w9, co
 #pragma unroll
     for (int r = 0; r < 2 * RS + 4; ++r) {
         const int iy = iy_first + r;
-        u64 v[6];
+        u64 v[8];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) v[j] = vn[j];
+        for (int j = 0; j < 8; ++j) v[j] = vn[j];
         if (r + 1 < 2 * RS + 4) fetch_row(r + 1);
-        // scatter this input row into the three depthwise rows it feeds: ky = 2 -> row iy-1 (slot (r+1)%3, completes),
-        // ky = 1 -> row iy (slot (r+2)%3), ky = 0 -> row iy+1 (slot r%3, starts from the bias)
+        // ky = 2 -> depthwise row iy-1 (slot (r+1)%3, completes), ky = 1 -> row iy (slot (r+2)%3), ky = 0 -> row iy+1 (slot r%3)
 #pragma unroll
-        for (int tx = 0; tx < 4; ++tx) {
+        for (int tx = 0; tx < 6; ++tx) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 dw[(r + 1) % 3][tx] = ffma2(wv[6 + kx], v[tx + kx], dw[(r + 1) % 3][tx]);
@@ -293,30 +290,39 @@ dw3x3_down_kernel(const float* __restrict__ in, const float* __restrict__ w9, co
             const int tyB = (q & 1) ? 1 : 0, tyA = tyB + 2;
             if (gy >= 0 && gy < H) {
 #pragma unroll
-                for (int tx = 0; tx < 4; ++tx) {
+                for (int tx = 0; tx < 6; ++tx) {
                     if (!dwok[tx]) continue;
                     const u64 d = lrelu_agc2(dw[(r + 1) % 3][tx]);
-                    accB = ffma2(firp[(tyB * 4 + tx) * fstride], d, accB);
-                    accA = ffma2(firp[(tyA * 4 + tx) * fstride], d, accA);
+                    if (tx < 4) {                         // tap column tx of output ox0
+                        accB[0] = ffma2(firp[(tyB * 4 + tx) * fstride], d, accB[0]);
+                        accA[0] = ffma2(firp[(tyA * 4 + tx) * fstride], d, accA[0]);
+                    }
+                    if (tx >= 2) {                        // tap column tx-2 of output ox0+1
+                        accB[1] = ffma2(firp[(tyB * 4 + tx - 2) * fstride], d, accB[1]);
+                        accA[1] = ffma2(firp[(tyA * 4 + tx - 2) * fstride], d, accA[1]);
+                    }
                 }
             }
             if ((q & 1) && q >= 3) {                      // gy = 2k even: last tap of output row k-1 = oy0 + (q-3)/2
                 const int orow = oy0 + ((q - 3) >> 1);
-                const size_t o = ((img * H2 + orow) * W2 + ox) * (size_t)C + c;
-                const float2 ov = unpk2(accA);
-                if (out_f32) *reinterpret_cast<float2*>(out_f32 + o) = ov;
-                if (out_hi) {
-                    __half h0, l0, h1, l1;
-                    split_f16(ov.x, kActSplitScale, h0, l0);
-                    split_f16(ov.y, kActSplitScale, h1, l1);
-                    *reinterpret_cast<__half2*>(out_hi + o) = __halves2half2(h0, h1);
-                    *reinterpret_cast<__half2*>(out_lo + o) = __halves2half2(l0, l1);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const size_t o = ((img * H2 + orow) * W2 + ox0 + e) * (size_t)C + c;
+                    const float2 ov = unpk2(accA[e]);
+                    if (out_f32) *reinterpret_cast<float2*>(out_f32 + o) = ov;
+                    if (out_hi) {
+                        __half h0, l0, h1, l1;
+                        split_f16(ov.x, kActSplitScale, h0, l0);
+                        split_f16(ov.y, kActSplitScale, h1, l1);
+                        *reinterpret_cast<__half2*>(out_hi + o) = __halves2half2(h0, h1);
+                        *reinterpret_cast<__half2*>(out_lo + o) = __halves2half2(l0, l1);
+                    }
                 }
             }
-            if (q & 1) { accA = accB; accB = 0ull; }
+            if (q & 1) { accA[0] = accB[0]; accA[1] = accB[1]; accB[0] = 0ull; accB[1] = 0ull; }
         }
 #pragma unroll
-        for (int tx = 0; tx < 4; ++tx) dw[(r + 1) % 3][tx] = bv;   // slot is reused by depthwise row iy + 2
+        for (int tx = 0; tx < 6; ++tx) dw[(r + 1) % 3][tx] = bv;   // slot is reused by depthwise row iy + 2
     }
 }
 
@@ -327,7 +333,7 @@ cudaError_t launch_dw3x3_down(const float* in, const float* w9, const float* bia
                               int n, int H, int W, int C, cudaStream_t s) {
     const int H2 = H / 2, W2 = W / 2;
     const int rs = (H2 >= 8) ? 8 : 4, strips = H2 / rs;
-    const size_t per_img = (size_t)strips * W2 * (C / 2);
+    const size_t per_img = (size_t)strips * (W2 / 2) * (C / 2);
     return for_image_groups(n, per_img, [&](int i0, int cnt) {
         const uint32_t items = (uint32_t)(per_img * cnt);
         const size_t oi = (size_t)i0 * H * W * C, oo = (size_t)i0 * H2 * W2 * C;
