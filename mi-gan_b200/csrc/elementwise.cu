@@ -94,90 +94,6 @@ cudaError_t launch_stem(const float* x, const float* w, const float* b, float* o
 // depthwise 3x3 + bias + act, NHWC -> NHWC (used by the CUDA-core path; the tcgen05 path
 // fuses this stage into the GEMM prologue)
 // --------------------------------------------------------------------------------------
-// Thread = (4 channels, column x, strip of RS rows): the 9 taps + bias stay in registers and a 3x3 window slides
-// down the strip (3 L1-served 128-bit loads per output vector instead of 9 + 9 tap loads).
-template <int RS>
-__global__ void __launch_bounds__(256)
-dw3x3_act_kernel(const float* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ bias,
-                 float* __restrict__ out, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                 uint32_t items, int lw, int lh, int lcv, int lstrips) {
-    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
-    if (idx >= items) return;
-    const int W = 1 << lw, H = 1 << lh, C = 4 << lcv;
-    const int c = (int)(idx & ((1u << lcv) - 1)) * 4;
-    uint32_t t = idx >> lcv;
-    const int x = (int)(t & (W - 1));
-    t >>= lw;
-    const int strip = (int)(t & ((1u << lstrips) - 1));
-    const size_t img = t >> lstrips;
-    const int y0 = strip * RS;
-    float4 w[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) w[k] = ldg4(w9 + k * C + c);
-    const float4 bv = ldg4(bias + c);
-    const float* base = in + img * (size_t)H * W * C + c;
-    const bool okl = x > 0, okr = x + 1 < W;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto load_row = [&](int y, float4 (&r)[3]) {
-        if (y < 0 || y >= H) { r[0] = r[1] = r[2] = zero; return; }
-        const float* p = base + ((size_t)y * W + x) * C;
-        r[0] = okl ? ldg4(p - C) : zero;
-        r[1] = ldg4(p);
-        r[2] = okr ? ldg4(p + C) : zero;
-    };
-    float4 r0[3], r1[3], r2[3], rn[3];
-    load_row(y0 - 1, r0);
-    load_row(y0, r1);
-    load_row(y0 + 1, r2);
-#pragma unroll
-    for (int i = 0; i < RS; ++i) {
-        const int y = y0 + i;
-        if (i + 1 < RS) load_row(y + 2, rn);              // next iteration's bottom row: issued one iteration ahead
-        float4 acc = bv;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) { fma4(acc, w[d], r0[d]); fma4(acc, w[3 + d], r1[d]); fma4(acc, w[6 + d], r2[d]); }
-        acc = lrelu_agc4(acc);
-        const size_t o = ((img * H + y) * (size_t)W + x) * C + c;
-        if (out) stg4(out + o, acc);
-        if (out_hi) {   // pre-split A operand for the tcgen05 GEMM (layers whose Cout spans several CTA N tiles)
-            __half h[4], l[4];
-            split_f16(acc.x, kActSplitScale, h[0], l[0]);
-            split_f16(acc.y, kActSplitScale, h[1], l[1]);
-            split_f16(acc.z, kActSplitScale, h[2], l[2]);
-            split_f16(acc.w, kActSplitScale, h[3], l[3]);
-            *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(h);
-            *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(l);
-        }
-#pragma unroll
-        for (int d = 0; d < 3; ++d) { r0[d] = r1[d]; r1[d] = r2[d]; r2[d] = rn[d]; }
-    }
-}
-
-cudaError_t launch_dw3x3(const float* in, const float* w9, const float* bias, float* out, __half* out_hi, __half* out_lo,
-                         int n, int H, int W, int C, cudaStream_t s) {
-    const int rs = (H >= 8) ? 8 : 4, strips = H / rs;
-    const size_t per_img = (size_t)strips * W * (C / 4);
-    return for_image_groups(n, per_img, [&](int i0, int cnt) {
-        const uint32_t items = (uint32_t)(per_img * cnt);
-        const size_t off = (size_t)i0 * H * W * C;
-        auto kern = (rs == 8) ? dw3x3_act_kernel<8> : dw3x3_act_kernel<4>;
-        kern<<<(items + 255) / 256, 256, 0, s>>>(in + off, w9, bias, out ? out + off : nullptr, out_hi ? out_hi + off : nullptr,
-                                                out_lo ? out_lo + off : nullptr, items, host_log2(W), host_log2(H), host_log2(C / 4),
-                                                host_log2(strips));
-    });
-}
-
-// --------------------------------------------------------------------------------------
-// depthwise 3x3 + bias + act + FIR 4x4 / stride 2 / pad 1 (SeparableConv2d.conv1 + Downsample2d).
-//
-// Thread = (channel PAIR, low-res column ox, strip of RS low-res rows).  It walks down the hi-res
-// input rows once, keeping a rolling 3-row x 6-column window in registers (L1-served 64-bit loads,
-// a warp reads 256 contiguous bytes per pixel), evaluates each activated depthwise value of its 4
-// columns exactly once per row and scatters it into the two FIR accumulators it contributes to
-// (rows 2oy-1..2oy+2 feed output oy).  All MACs are packed FFMA2 (two channels per instruction).
-// Depthwise outputs outside the image are ZERO (the FIR zero-pads the ACTIVATED tensor,
-// migan_inference.py:62-70), not act(bias).
-// --------------------------------------------------------------------------------------
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk2(float lo, float hi) {
     u64 d;
@@ -200,6 +116,96 @@ __device__ __forceinline__ u64 lrelu_agc2(u64 v) {
     return pk2(fminf(fmaxf(m.x, -kActClamp), kActClamp), fminf(fmaxf(m.y, -kActClamp), kActClamp));
 }
 
+// Thread = (channel PAIR, PAIR of adjacent columns x0 = 2*xp, x0 + 1, strip of RS rows): the 9 taps + bias stay in
+// registers, a 3-row x 4-column window slides down the strip (4 L1-served 64-bit loads per row feed 2 outputs),
+// all MACs are packed FFMA2, and the next row is fetched one iteration ahead.
+template <int RS>
+__global__ void __launch_bounds__(256)
+dw3x3_act_kernel(const float* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ bias,
+                 float* __restrict__ out, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                 uint32_t items, int lw, int lh, int lcp, int lstrips) {
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    if (idx >= items) return;
+    const int W = 1 << lw, H = 1 << lh, C = 2 << lcp;
+    const int c = (int)(idx & ((1u << lcp) - 1)) * 2;
+    uint32_t t = idx >> lcp;
+    const int x0 = (int)(t & ((W >> 1) - 1)) * 2;
+    t >>= (lw - 1);
+    const int strip = (int)(t & ((1u << lstrips) - 1));
+    const size_t img = t >> lstrips;
+    const int y0 = strip * RS;
+    u64 w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[k] = ldg2(w9 + k * C + c);
+    const u64 bv = ldg2(bias + c);
+    const float* base = in + img * (size_t)H * W * C + c;
+    const bool okl = x0 > 0, okr = x0 + 2 < W;
+    auto load_row = [&](int y, u64 (&r)[4]) {
+        if (y < 0 || y >= H) { r[0] = r[1] = r[2] = r[3] = 0ull; return; }
+        const float* p = base + ((size_t)y * W + x0) * C;
+        r[0] = okl ? ldg2(p - C) : 0ull;
+        r[1] = ldg2(p);
+        r[2] = ldg2(p + C);
+        r[3] = okr ? ldg2(p + 2 * C) : 0ull;
+    };
+    u64 r0[4], r1[4], r2[4], rn[4];
+    load_row(y0 - 1, r0);
+    load_row(y0, r1);
+    load_row(y0 + 1, r2);
+#pragma unroll
+    for (int i = 0; i < RS; ++i) {
+        const int y = y0 + i;
+        if (i + 1 < RS) load_row(y + 2, rn);              // next iteration's bottom row: issued one iteration ahead
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {                     // the two output columns
+            u64 acc = bv;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                acc = ffma2(w[d], r0[e + d], acc);
+                acc = ffma2(w[3 + d], r1[e + d], acc);
+                acc = ffma2(w[6 + d], r2[e + d], acc);
+            }
+            const float2 v = unpk2(lrelu_agc2(acc));
+            const size_t o = ((img * H + y) * (size_t)W + x0 + e) * C + c;
+            if (out) *reinterpret_cast<float2*>(out + o) = v;
+            if (out_hi) {   // pre-split A operand for the tcgen05 GEMM (layers whose Cout spans several CTA N tiles)
+                __half h0, l0, h1, l1;
+                split_f16(v.x, kActSplitScale, h0, l0);
+                split_f16(v.y, kActSplitScale, h1, l1);
+                *reinterpret_cast<__half2*>(out_hi + o) = __halves2half2(h0, h1);
+                *reinterpret_cast<__half2*>(out_lo + o) = __halves2half2(l0, l1);
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) { r0[d] = r1[d]; r1[d] = r2[d]; r2[d] = rn[d]; }
+    }
+}
+
+cudaError_t launch_dw3x3(const float* in, const float* w9, const float* bias, float* out, __half* out_hi, __half* out_lo,
+                         int n, int H, int W, int C, cudaStream_t s) {
+    const int rs = (H >= 8) ? 8 : 4, strips = H / rs;
+    const size_t per_img = (size_t)strips * (W / 2) * (C / 2);
+    return for_image_groups(n, per_img, [&](int i0, int cnt) {
+        const uint32_t items = (uint32_t)(per_img * cnt);
+        const size_t off = (size_t)i0 * H * W * C;
+        auto kern = (rs == 8) ? dw3x3_act_kernel<8> : dw3x3_act_kernel<4>;
+        kern<<<(items + 255) / 256, 256, 0, s>>>(in + off, w9, bias, out ? out + off : nullptr, out_hi ? out_hi + off : nullptr,
+                                                out_lo ? out_lo + off : nullptr, items, host_log2(W), host_log2(H), host_log2(C / 2),
+                                                host_log2(strips));
+    });
+}
+
+// --------------------------------------------------------------------------------------
+// depthwise 3x3 + bias + act + FIR 4x4 / stride 2 / pad 1 (SeparableConv2d.conv1 + Downsample2d).
+//
+// Thread = (channel PAIR, low-res column ox, strip of RS low-res rows).  It walks down the hi-res
+// input rows once, keeping a rolling 3-row x 6-column window in registers (L1-served 64-bit loads,
+// a warp reads 256 contiguous bytes per pixel), evaluates each activated depthwise value of its 4
+// columns exactly once per row and scatters it into the two FIR accumulators it contributes to
+// (rows 2oy-1..2oy+2 feed output oy).  All MACs are packed FFMA2 (two channels per instruction).
+// Depthwise outputs outside the image are ZERO (the FIR zero-pads the ACTIVATED tensor,
+// migan_inference.py:62-70), not act(bias).
+// --------------------------------------------------------------------------------------
 // RS = low-res rows per thread (template: the row walk is fully unrolled).  Thread = (channel pair, PAIR of adjacent
 // low-res columns ox0 = 2*oxp, ox0 + 1, strip of RS rows).  Register plan per thread:
 //   v[8]       the current input row (columns 2ox0-2 .. 2ox0+5), fetched one row ahead (software pipelining)
