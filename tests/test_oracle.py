@@ -97,3 +97,45 @@ def test_op_oracles_match_golden():
             got = O.bias_act_ref(x, bvec, dim=1, act=act, clamp=clamp)
             assert np.allclose(got.numpy().ravel(), z["ba%d" % i], atol=1e-6), act
             i += 1
+
+
+# --------------------------------------------------------------------------- #
+# Co-Mod-GAN oracle (oracle/comodgan_oracle.py) against the fixtures the real reference produced
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("name", ["comodgan_R16_n2_w1", "comodgan_R32_n2_w3", "comodgan_R64_n1_w1"])
+def test_comodgan_oracle_reproduces_reference_fixture(name):
+    from oracle import comodgan_oracle as C
+    from oracle import migan_oracle as O
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    R, N = int(g["resolution"]), int(g["n"])
+    sd = C.make_state_dict(R, seed=int(g["wseed"]))
+    x = O.make_input(R, N, seed=int(g["xseed"]))
+    z = C.make_latent(N, seed=int(g["xseed"]) + 1)
+    assert abs(float(x.double().abs().sum()) - float(g["x_checksum"])) < 1e-6 * float(g["x_checksum"])
+    cutoff = None if int(g["cutoff"]) < 0 else int(g["cutoff"])
+    y = C.generator_forward(sd, x, z, R, truncation_psi=float(g["psi"]), truncation_cutoff=cutoff)
+    assert float((y - torch.from_numpy(g["y"])).abs().max()) <= 1e-4   # same primitives; allows a different BLAS build
+    y0 = C.generator_forward(sd, x, z, R, truncation_psi=float(g["psi"]), truncation_cutoff=cutoff, noise_mode="none")
+    assert float((y0 - torch.from_numpy(g["y_noise_none"])).abs().max()) <= 1e-4
+
+
+def test_comodgan_state_dict_spec_counts():
+    from oracle import comodgan_oracle as C
+    spec = C.state_dict_spec(256)
+    assert len(spec) == 180                                          # SURVEY: reference state_dict @256
+    assert sum(int(np.prod(s)) for s in spec.values()) == 79353026   # 79 M parameters + buffers
+    assert C.num_ws(256) == 14 and C.num_ws(512) == 16               # comodgan.py:371-374
+
+
+def test_conv2d_resample_oracle_reproduces_reference_vectors():
+    from oracle import comodgan_oracle as C
+    from oracle import migan_oracle as O
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "conv2d_resample.npz"))
+    f = O.setup_filter([1, 3, 3, 1])
+    names = sorted({k.rsplit(".", 1)[0] for k in g.files})
+    assert len(names) == 9
+    for name in names:
+        up, down, groups, flipw, p0, p1, p2, p3 = [int(v) for v in g[name + ".args"]]
+        y = C.conv2d_resample_ref(torch.from_numpy(g[name + ".x"]), torch.from_numpy(g[name + ".w"]), f=f, up=up,
+                                  down=down, padding=[p0, p1, p2, p3], groups=groups, flip_weight=bool(flipw))
+        assert float((y - torch.from_numpy(g[name + ".y"])).abs().max()) <= 1e-4, name
