@@ -40,7 +40,37 @@ SYMBOLS = [
     ("b200_bias_act", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_float, c_float, c_void_p]),
 ]
 
+# Every symbol include/comodgan_b200.h declares
+COMOD_SYMBOLS = [
+    ("comodgan_last_error", c_char_p, []),
+    ("comodgan_create", c_int, [c_int, c_int, POINTER(c_void_p)]),
+    ("comodgan_destroy", c_int, [c_void_p]),
+    ("comodgan_num_weights", c_int, [c_void_p]),
+    ("comodgan_weight_info", c_int, [c_void_p, c_int, POINTER(c_char_p), POINTER(c_int), POINTER(c_int64)]),
+    ("comodgan_set_weight", c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    ("comodgan_finalize_weights", c_int, [c_void_p]),
+    ("comodgan_workspace_bytes", c_size_t, [c_void_p, c_int]),
+    ("comodgan_num_noise_planes", c_int, [c_void_p]),
+    ("comodgan_noise_plane_res", c_int, [c_void_p, c_int]),
+    ("comodgan_forward", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_void_p,
+                                 c_void_p, c_size_t, c_void_p]),
+    ("comodgan_last_launch_count", c_int, [c_void_p]),
+    ("comodgan_set_tap", c_int, [c_void_p, c_char_p, c_void_p]),
+    ("b200_conv2d_resample", c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 18 +
+     [c_void_p, c_size_t, POINTER(c_size_t), POINTER(c_int), POINTER(c_int), c_void_p]),
+]
+
 _lib = None
+
+
+def bind(lib, symbols):
+    """Set restype / argtypes for `symbols` on an already dlopen-ed library (AttributeError if an export is missing)."""
+    for name, restype, argtypes in symbols:
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return lib
+
 
 
 class MiganError(RuntimeError):
@@ -69,10 +99,8 @@ def load(build_if_missing: bool = False):
                 "migan_b200: %s not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). There is no CPU / pure-PyTorch fallback." % path)
     lib = ctypes.CDLL(path)
-    for name, restype, argtypes in SYMBOLS:
-        fn = getattr(lib, name)  # AttributeError if the export is missing
-        fn.restype = restype
-        fn.argtypes = argtypes
+    bind(lib, SYMBOLS)
+    bind(lib, COMOD_SYMBOLS)
     _lib = lib
     return lib
 
@@ -80,4 +108,10 @@ def load(build_if_missing: bool = False):
 def check(rc: int) -> None:
     if rc != 0:
         msg = load().migan_last_error()
+        raise MiganError(rc, msg.decode() if msg else "unknown error")
+
+
+def check_comod(rc: int, lib=None) -> None:
+    if rc != 0:
+        msg = (lib or load()).comodgan_last_error()
         raise MiganError(rc, msg.decode() if msg else "unknown error")

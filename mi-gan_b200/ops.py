@@ -26,6 +26,10 @@ def _stream(t: torch.Tensor):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+def _guard(device: torch.device):
+    return torch.cuda.device(device)
+
+
 def _require_cuda_f32(x: torch.Tensor, what: str) -> torch.Tensor:
     if not isinstance(x, torch.Tensor):
         raise TypeError("%s must be a torch.Tensor" % what)
@@ -182,25 +186,55 @@ def _conv1x1(x, w):
     return y.permute(0, 3, 1, 2).contiguous()
 
 
+def _conv2d_resample_general(x, w, f, up, down, padding, groups, flip_weight, flip_filter):
+    """All six branches through the C ABI (`b200_conv2d_resample`, include/comodgan_b200.h): NHWC im2col + fp32 GEMM,
+    transposed convolution as GEMM + col2im, NHWC upfirdn2d.  `padding` is the caller's (un-adjusted) padding."""
+    lib = _abi.load()
+    n, cin, h, wd = x.shape
+    cout, _, kh, kw = w.shape
+    if f is None:
+        f2d, fh, fw = None, 0, 0
+    else:
+        f = f.to(device=x.device, dtype=torch.float32)
+        f2d = (torch.outer(f, f) if f.ndim == 1 else f).contiguous()       # separable == outer product (upfirdn2d.py:239-240)
+        fh, fw = f2d.shape
+    px0, px1, py0, py1 = padding
+    args = [n, cin, h, wd, cout, kh, kw, fh, fw, up, down, px0, px1, py0, py1, groups, int(bool(flip_weight)), int(bool(flip_filter))]
+    need, oh, ow = ctypes.c_size_t(), ctypes.c_int(), ctypes.c_int()
+    _abi.check_comod(lib.b200_conv2d_resample(None, None, None, None, *args, None, 0, ctypes.byref(need), ctypes.byref(oh),
+                                              ctypes.byref(ow), None))
+    y = torch.empty((n, cout, oh.value, ow.value), dtype=torch.float32, device=x.device)
+    raw = torch.empty(need.value + 1024, dtype=torch.uint8, device=x.device)
+    off = (-raw.data_ptr()) % 1024
+    with _guard(x.device):
+        _abi.check_comod(lib.b200_conv2d_resample(x.data_ptr(), w.data_ptr(), f2d.data_ptr() if f2d is not None else None,
+                                                  y.data_ptr(), *args, raw.data_ptr() + off, need.value, None, None, None,
+                                                  _stream(x)))
+    return y
+
+
 def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
-    """2-D convolution with optional up/down-sampling (torch_utils/ops/conv2d_resample.py:59-154).
-    Implemented: the 1x1-kernel branches the MI-GAN graph uses (:106-116 and the plain case :145-147).
-    k x k kernels (Co-Mod-GAN teacher) are not built yet and raise NotImplementedError."""
+    """2-D convolution with optional up/down-sampling (torch_utils/ops/conv2d_resample.py:59-154), every branch:
+    1x1 + down (:106-109), 1x1 + up (:112-115), k x k down (:118-121), up via transposed convolution (:124-142),
+    plain (:145-147) and the generic fallback (:150-154); `groups` included."""
     x = _require_cuda_f32(x, "x")
     w = _require_cuda_f32(w, "w")
     assert x.ndim == 4 and w.ndim == 4
     assert isinstance(up, int) and up >= 1 and isinstance(down, int) and down >= 1 and groups >= 1
+    assert f is None or (isinstance(f, torch.Tensor) and f.ndim in [1, 2] and f.dtype == torch.float32)
     out_channels, in_channels_per_group, kh, kw = w.shape
+    assert x.shape[1] == in_channels_per_group * groups and out_channels % groups == 0
+    pad = list(_parse_padding(padding))
+    fast_1x1 = (kh == 1 and kw == 1 and groups == 1 and x.shape[1] % 16 == 0 and out_channels % 64 == 0)
+    if not fast_1x1:
+        return _conv2d_resample_general(x, w, f, up, down, pad, groups, flip_weight, flip_filter)
+    # MI-GAN's 1x1 branches: channels-last GEMM straight on the tensor (no im2col)
     fw, fh = _get_filter_size(f)
-    px0, px1, py0, py1 = _parse_padding(padding)
+    px0, px1, py0, py1 = pad
     if up > 1:   # conv2d_resample.py:94-98
         px0 += (fw + up - 1) // 2; px1 += (fw - up) // 2; py0 += (fh + up - 1) // 2; py1 += (fh - up) // 2
     if down > 1:  # :101-104
         px0 += (fw - down + 1) // 2; px1 += (fw - down) // 2; py0 += (fh - down + 1) // 2; py1 += (fh - down) // 2
-    if kh != 1 or kw != 1 or groups != 1:
-        raise NotImplementedError("migan_b200.ops.conv2d_resample: only 1x1 kernels with groups=1 are built (MI-GAN path)")
-    if x.shape[1] % 4 or out_channels % 64 or x.shape[1] % 16:
-        raise NotImplementedError("conv2d_resample 1x1: Cin must be a multiple of 16 and Cout of 64")
     if down > 1 and up == 1:    # :106-110  FIR-down, then conv
         x = upfirdn2d(x, f, down=down, padding=[px0, px1, py0, py1], flip_filter=flip_filter)
         return _conv1x1(x, w)
@@ -209,9 +243,4 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         return upfirdn2d(x, f, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
     if up == 1 and down == 1 and [px0, px1, py0, py1] == [0, 0, 0, 0]:   # :145-147
         return _conv1x1(x, w)
-    # generic fallback order (:150-154): up-FIR, conv, down-sample
-    x = upfirdn2d(x, (f if up > 1 else None), up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
-    x = _conv1x1(x, w)
-    if down > 1:
-        x = upfirdn2d(x, f, down=down, flip_filter=flip_filter)
-    return x
+    return _conv2d_resample_general(x, w, f, up, down, pad, groups, flip_weight, flip_filter)

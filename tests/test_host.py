@@ -96,3 +96,53 @@ def test_arch_helpers():
     assert arch.encoder_resolutions(256) == [256, 128, 64, 32, 16, 8, 4]
     assert arch.synthesis_resolutions(64) == [4, 8, 16, 32, 64]
     assert [arch.nf(r) for r in (512, 256, 128, 64, 4)] == [64, 128, 256, 512, 512]
+
+
+# --------------------------------------------------------------------------- #
+# Co-Mod-GAN boundary (include/comodgan_b200.h, migan_b200.comodgan)
+# --------------------------------------------------------------------------- #
+def test_library_exports_every_comodgan_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "comodgan_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b((?:comodgan|b200)_[a-z0-9_]+)\s*\(", header))
+    bound = {name for name, _, _ in _abi.COMOD_SYMBOLS}
+    assert declared == bound, declared ^ bound
+    for name in declared:
+        assert hasattr(lib, name)
+
+
+@pytest.mark.parametrize("R", [16, 256, 512])
+def test_comodgan_state_dict_layout_matches_reference_order(lib, R):
+    """Python modules, C registry and the oracle spec (checked against the real reference by
+    make_golden_comodgan.py with strict=True) agree on names, order and shapes."""
+    from migan_b200 import comodgan
+    from oracle import comodgan_oracle as C
+    spec = C.state_dict_spec(R)
+    g = comodgan.Generator(comodgan.Mapping(num_ws=C.num_ws(R)), comodgan.Encoder(resolution=R),
+                           comodgan.Synthesis(resolution=R))
+    sd = g.state_dict()
+    assert list(sd.keys()) == list(spec.keys())
+    for k, shape in spec.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    params = {k for k, _ in g.named_parameters()}
+    assert "mapping.w_avg" not in params and "synthesis.b4.conv.noise_const" not in params
+    assert "synthesis.b4.conv.noise_strength" in params and "encoder.b4.fc.weight" in params
+    g.load_state_dict(C.make_state_dict(R) if R == 16 else sd, strict=True)
+    assert g.num_ws == C.num_ws(R) and g.img_resolution == R and g.z_dim == 512
+
+
+def test_comodgan_constructor_and_cpu_errors(lib):
+    from migan_b200 import comodgan
+    with pytest.raises(ValueError):
+        comodgan.Encoder(resolution=48)
+    with pytest.raises(ValueError):     # num_ws mismatch (stylegan.py:580-581)
+        comodgan.Generator(comodgan.Mapping(num_ws=16), comodgan.Encoder(resolution=256), comodgan.Synthesis(resolution=256))
+    g = comodgan.Generator(comodgan.Mapping(num_ws=6), comodgan.Encoder(resolution=16), comodgan.Synthesis(resolution=16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        g(torch.zeros(1, 4, 16, 16))
+    with pytest.raises(RuntimeError, match="shape"):
+        g(torch.zeros(1, 3, 16, 16))
+    h = ctypes.c_void_p()
+    assert lib.comodgan_create(16, -1, ctypes.byref(h)) == 0
+    assert lib.comodgan_finalize_weights(h) != 0        # no device, no weights: fails loudly
+    lib.comodgan_destroy(h)
