@@ -37,12 +37,19 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--res", type=int, default=512)
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU")
+    ap.add_argument("--workload", default="migan", choices=["migan", "comodgan"],
+                    help="migan (default: BASELINE.json metric, configs[2]/[3]) or comodgan (configs[4], 256 / 16 images)")
+    ap.add_argument("--res", type=int, default=None, help="default 512 (migan) / 256 (comodgan)")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU; default 32 (migan) / 16 (comodgan)")
     ap.add_argument("--path", default=os.environ.get("MIGAN_B200_PATH", "tc"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-launch table (JSON) here")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.res is None:
+        args.res = 512 if args.workload == "migan" else 256
+    if args.batch is None:
+        args.batch = 32 if args.workload == "migan" else 16
+    return args
 
 
 # ------------------------------------------------------------------------------------------
@@ -275,6 +282,26 @@ def run_b200(args):
     e2e = {"value": world * B * K / e2e_s, "unit": "images/s",
            "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4}
 
+    # ---- same, through the uint8 request call (img + mask uint8 in, composed uint8 out: 7 B/px over PCIe, not 28) ----
+    e2e_u8 = None
+    if world == 1:
+        try:
+            g8 = torch.Generator().manual_seed(7)
+            img8 = torch.randint(0, 256, (B, R, R, 3), dtype=torch.uint8, generator=g8).pin_memory()
+            m8 = ((torch.rand(B, R, R, generator=g8) > 0.4).to(torch.uint8) * 255).pin_memory()
+            o8 = torch.empty((B, R, R, 3), dtype=torch.uint8).pin_memory()
+            for _ in range(2):
+                model.forward_u8(img8, m8, out=o8)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(K):
+                model.forward_u8(img8, m8, out=o8)        # synchronous: o8 is complete on return
+            u8_s = time.perf_counter() - t0
+            e2e_u8 = {"value": B * K / u8_s, "unit": "images/s", "h2d_bytes_per_step": img8.numel() + m8.numel(),
+                      "d2h_bytes_per_step": o8.numel(), "api": "Generator.forward_u8 (migan_forward_u8)"}
+        except Exception as exc:  # the uint8 path is an extra; the contract's e2e above does not depend on it
+            e2e_u8 = {"error": str(exc)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -344,13 +371,122 @@ def run_b200(args):
                    "kernel_timing": "separate pass of K steps with cudaEvents around every launch",
                    "e2e": "K host batches submitted back to back through migan_forward_host_async (pinned H2D + forward + D2H "
                           "per batch, two staging slots, two micro-batches), timed until the last output landed in host memory"},
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8,
         "gpu_launches": launches_per_step * K,
     }
     print_json(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def comodgan_gemm_flops(R: int) -> float:
+    """2 x MACs of every GEMM one image goes through (closed form over the layer list of comodgan.py)."""
+    ch = lambda r: min(32768 // r, 512)
+    macs = 8 * 512 * 512 + 4 * ch(R) * R * R                          # mapping, fromrgb
+    r = R
+    while r >= 8:
+        macs += 9 * ch(r) * ch(r) * r * r + 9 * ch(r) * ch(r // 2) * (r // 2) ** 2      # encoder conv0, conv1 (stride 2)
+        r //= 2
+    macs += 9 * 512 * 512 * 16 + 2 * 8192 * 1024                      # b4 conv, the two bottleneck dense layers
+    macs += 9 * 512 * 512 * 16 + 512 * 3 * 16 + 2 * 1536 * 512        # synthesis b4 conv, torgb, affines
+    r = 8
+    while r <= R:
+        macs += 9 * ch(r // 2) * ch(r) * (r // 2) ** 2 + 9 * ch(r) * ch(r) * r * r + 3 * ch(r) * r * r   # conv0 (transposed), conv1, torgb
+        macs += 1536 * (ch(r // 2) + 2 * ch(r))
+        r *= 2
+    return 2.0 * macs
+
+
+def run_comodgan(args):
+    """BASELINE.json configs[4]: comodgan-256 Generator forward, batch 16, noise_mode='const'.  Round-1 path: exact fp32
+    CUDA-core GEMMs (no tensor cores yet), so the roofline fraction against the tensor peak is small by construction."""
+    from migan_b200 import comodgan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    R, B, K, Wm = args.res, args.batch, args.steps, max(args.warmup, 3)
+    num_ws = 2 * (R.bit_length() - 1) - 2
+    torch.manual_seed(1)
+    model = comodgan.Generator(comodgan.Mapping(num_ws=num_ws), comodgan.Encoder(resolution=R), comodgan.Synthesis(resolution=R))
+    with torch.no_grad():
+        for k, p in model.named_parameters():                          # non-trivial biases / noise, like the parity tests
+            if k.endswith("noise_strength") or (k.endswith(".bias") and "affine" not in k):
+                p.copy_(0.1 * torch.randn(p.shape))
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(1234 + rank)
+    mask = (torch.rand(B, 1, R, R, generator=g) > 0.4).float()
+    img = torch.rand(B, 3, R, R, generator=g) * 2 - 1
+    x_host = torch.cat([mask - 0.5, img * mask], 1).pin_memory()
+    z_host = torch.randn(B, 512, generator=g).pin_memory()
+    x, z = x_host.to(dev), z_host.to(dev)
+    for _ in range(Wm):
+        model(x, z=z, noise_mode="const")
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        y = model(x, z=z, noise_mode="const")
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    y_host = torch.empty((B, 3, R, R), dtype=torch.float32).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        y = model(x_host.to(dev, non_blocking=True), z=z_host.to(dev, non_blocking=True), noise_mode="const")
+        y_host.copy_(y, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if rank != 0:
+        return
+    flops = comodgan_gemm_flops(R) * B
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    tpeak = float(peaks.get("bf16_tflops_sustained", 0) or 0) or 1392.6
+    achieved = flops / (elapsed_ms / K * 1e-3) / 1e12
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import comodgan_oracle as C  # checker / CPU baseline only
+        from oracle import migan_oracle as O
+        pick_cpu_threads(R)
+        sd = C.make_state_dict(R, seed=1)
+        xc, zc = O.make_input(R, 1, seed=1234), C.make_latent(1, seed=1235)
+        C.generator_forward(sd, xc, zc, R)
+        times = []
+        while len(times) < 10 and (sum(times) < 10.0 or not times):
+            t1 = time.perf_counter()
+            C.generator_forward(sd, xc, zc, R)
+            times.append(time.perf_counter() - t1)
+        cpu = {"value": len(times) / sum(times), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "%d bs=1 forwards of comodgan-%d with the oracle port (torch %s CPU ops)" % (len(times), R, torch.__version__)}
+    line = {
+        "metric": "images/sec", "value": world * B * K / (elapsed_ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": K,
+        "warmup": Wm, "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "comodgan-%d Generator.forward (z given, noise_mode=const), %d images/GPU" % (R, B),
+                   "arithmetic": "exact fp32: im2col + CUDA-core GEMM (round-1 first path; tcgen05 implicit GEMM is the next step)",
+                   "global_batch": world * B, "weights": "constructor-style N(0,1) + non-zero biases / noise strengths",
+                   "l2": "col matrices are GBs per layer: far beyond the 126 MB L2"},
+        "roofline": {"bound": "tensor", "kernel": "pw_gemm_simt (all GEMM launches)", "achieved": achieved, "peak": tpeak,
+                     "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None,
+                     "note": "achieved = closed-form GEMM FLOPs of the step / whole step time (upper bound on the GEMM kernel's "
+                             "own time); peak = MEASURED_PEAKS.json bf16_tflops_sustained"},
+        "cpu_baseline": cpu, "clocks": clocks,
+        "e2e": {"value": world * B * K / e2e_s, "unit": "images/s", "h2d_bytes_per_step": (x_host.numel() + z_host.numel()) * 4,
+                "d2h_bytes_per_step": y_host.numel() * 4},
+        "gpu_launches": model.last_launch_count() * K,
+    }
+    print_json(json.dumps(line), flush=True)
 
 
 def main():
@@ -374,6 +510,8 @@ def main():
     print_json = emit
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "comodgan":
+        run_comodgan(args)
     else:
         run_b200(args)
 

@@ -9,6 +9,7 @@
  *                                     (key names + shapes = the reference state_dict)
  *   migan_forward                     Generator.forward(x)          lib/model_zoo/migan_inference.py:362-369
  *   migan_forward_host                scripts/demo.py:131-136 (x.to(device) -> model(x) -> .cpu())
+ *   migan_forward_u8, b200_pre/postprocess_u8   scripts/demo.py:56-66 (preprocess) and :135-142 (uint8 + mask composite)
  *   b200_upfirdn2d                    _plugin.upfirdn2d(...)        torch_utils/ops/upfirdn2d.cpp:16-94
  *   b200_bias_act                     _plugin.bias_act(...)         torch_utils/ops/bias_act.cpp:32-90 (grad == 0)
  *   b200_conv1x1_nhwc                 the F.conv2d of conv2d_resample's 1x1 branches  torch_utils/ops/conv2d_resample.py:106-116
@@ -84,6 +85,18 @@ int migan_forward_host(migan_ctx* ctx, const float* x_host, float* y_host, int n
 int migan_forward_host_async(migan_ctx* ctx, const float* x_host, float* y_host, int n,
                              void* workspace, size_t workspace_bytes, int path, void* stream);
 int migan_host_wait(migan_ctx* ctx);
+
+/* uint8 request path (the callers' pre/post-processing fused around the forward, scripts/demo.py:56-66 and :135-142):
+ * img_host u8 [n,R,R,3] (RGB, HWC), mask_host u8 [n,R,R] (255 = known pixel, anything else = hole) ->
+ * out_host u8 [n,R,R,3] = known pixels of img, generated pixels elsewhere.  7 bytes per pixel cross PCIe instead of 28.
+ * workspace_bytes must be >= migan_workspace_bytes(n) + migan_u8_staging_bytes(n).  Synchronous (out_host complete). */
+size_t migan_u8_staging_bytes(const migan_ctx* ctx, int n);
+int migan_forward_u8(migan_ctx* ctx, const uint8_t* img_host, const uint8_t* mask_host, uint8_t* out_host, int n,
+                     void* workspace, size_t workspace_bytes, int path, void* stream);
+/* The two kernels on their own (DEVICE pointers): x[n,4,r,r] = cat([mask-0.5, img*mask]) and the composite of y[n,3,r,r]. */
+int b200_preprocess_u8(const uint8_t* img_hwc, const uint8_t* mask_hw, float* x_nchw, int n, int r, void* stream);
+int b200_postprocess_u8(const float* y_nchw, const uint8_t* img_hwc, const uint8_t* mask_hw, uint8_t* out_hwc, int n, int r,
+                        void* stream);
 
 /* Kernels launched by the most recent migan_forward on this context. */
 int migan_last_launch_count(const migan_ctx* ctx);

@@ -28,6 +28,10 @@ SYMBOLS = [
     ("migan_forward_host", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     ("migan_forward_host_async", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     ("migan_host_wait", c_int, [c_void_p]),
+    ("migan_u8_staging_bytes", c_size_t, [c_void_p, c_int]),
+    ("migan_forward_u8", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    ("b200_preprocess_u8", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    ("b200_postprocess_u8", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     ("migan_last_launch_count", c_int, [c_void_p]),
     ("migan_set_profiling", c_int, [c_void_p, c_int]),
     ("migan_profile_num_steps", c_int, [c_void_p]),
@@ -59,6 +63,8 @@ COMOD_SYMBOLS = [
     ("b200_conv2d_resample", c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 18 +
      [c_void_p, c_size_t, POINTER(c_size_t), POINTER(c_int), POINTER(c_int), c_void_p]),
 ]
+
+PREPOST_SYMBOLS = [s for s in SYMBOLS if s[0] in ("b200_preprocess_u8", "b200_postprocess_u8")]
 
 _lib = None
 

@@ -52,4 +52,9 @@ cudaError_t launch_upfirdn2d(const float* x, const float* f, float* y, int n, in
 cudaError_t launch_bias_act(const float* x, const float* b, float* y, int64_t numel, int64_t step_b, int size_b,
                             int act, float alpha, float gain, float clamp, cudaStream_t s);
 
+// ---- uint8 pre/post-processing (prepost.cu): demo.py:56-66 and :135-142 around the forward ------
+int launch_preprocess_u8(const uint8_t* img_hwc, const uint8_t* mask_hw, float* x_nchw, int n, int r, cudaStream_t s);
+int launch_postprocess_u8(const float* y_nchw, const uint8_t* img_hwc, const uint8_t* mask_hw, uint8_t* out_hwc, int n, int r,
+                          cudaStream_t s);
+
 }  // namespace migan

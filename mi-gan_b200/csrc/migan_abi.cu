@@ -934,6 +934,53 @@ int migan_forward_host_async(migan_ctx* ctx, const float* x_host, float* y_host,
     return forward_host_enqueue(ctx, x_host, y_host, n, workspace, workspace_bytes, path, stream, nullptr);
 }
 
+size_t migan_u8_staging_bytes(const migan_ctx* ctx, int n) {
+    if (!ctx || n <= 0) return 0;
+    const size_t px = (size_t)n * ctx->resolution * ctx->resolution;
+    return align_up(4 * px * sizeof(float), 1024) + align_up(3 * px * sizeof(float), 1024) + 2 * align_up(3 * px, 1024) + align_up(px, 1024);
+}
+
+int migan_forward_u8(migan_ctx* ctx, const uint8_t* img_host, const uint8_t* mask_host, uint8_t* out_host, int n,
+                     void* workspace, size_t workspace_bytes, int path, void* stream) {
+    if (!ctx || !img_host || !mask_host || !out_host || !workspace) return fail(MIGAN_ERR_INVALID, "null argument");
+    if (n <= 0) return fail(MIGAN_ERR_INVALID, "batch size must be positive, got %d", n);
+    const size_t ws = migan_workspace_bytes(ctx, n);
+    if (workspace_bytes < ws + migan_u8_staging_bytes(ctx, n))
+        return fail(MIGAN_ERR_WORKSPACE, "workspace too small for uint8 staging: %zu < %zu bytes", workspace_bytes,
+                    ws + migan_u8_staging_bytes(ctx, n));
+    const int R = ctx->resolution;
+    const size_t px = (size_t)n * R * R;
+    unsigned char* b = static_cast<unsigned char*>(workspace) + ws;
+    float* xd = reinterpret_cast<float*>(b);               b += align_up(4 * px * sizeof(float), 1024);
+    float* yd = reinterpret_cast<float*>(b);               b += align_up(3 * px * sizeof(float), 1024);
+    uint8_t* img_d = b;                                     b += align_up(3 * px, 1024);
+    uint8_t* out_d = b;                                     b += align_up(3 * px, 1024);
+    uint8_t* mask_d = b;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(img_d, img_host, 3 * px, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(mask_d, mask_host, px, cudaMemcpyHostToDevice, st));
+    CUDA_TRY((cudaError_t)migan::launch_preprocess_u8(img_d, mask_d, xd, n, R, st));
+    if (int rc = migan_forward(ctx, xd, yd, n, workspace, ws, path, stream)) return rc;
+    CUDA_TRY((cudaError_t)migan::launch_postprocess_u8(yd, img_d, mask_d, out_d, n, R, st));
+    ctx->last_launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(out_host, out_d, 3 * px, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MIGAN_OK;
+}
+
+int b200_preprocess_u8(const uint8_t* img, const uint8_t* mask, float* x, int n, int r, void* stream) {
+    if (!img || !mask || !x || n <= 0 || r <= 0) return fail(MIGAN_ERR_INVALID, "preprocess_u8: bad arguments");
+    CUDA_TRY((cudaError_t)migan::launch_preprocess_u8(img, mask, x, n, r, static_cast<cudaStream_t>(stream)));
+    return MIGAN_OK;
+}
+
+int b200_postprocess_u8(const float* y, const uint8_t* img, const uint8_t* mask, uint8_t* out, int n, int r, void* stream) {
+    if (!y || !img || !mask || !out || n <= 0 || r <= 0) return fail(MIGAN_ERR_INVALID, "postprocess_u8: bad arguments");
+    CUDA_TRY((cudaError_t)migan::launch_postprocess_u8(y, img, mask, out, n, r, static_cast<cudaStream_t>(stream)));
+    return MIGAN_OK;
+}
+
 int migan_host_wait(migan_ctx* ctx) {
     if (!ctx) return fail(MIGAN_ERR_INVALID, "null ctx");
     if (!ctx->s_out) return MIGAN_OK;

@@ -213,6 +213,43 @@ class Generator(nn.Module):
             _abi.check(fn(eng.handle, x_host.data_ptr(), out.data_ptr(), n, ws.data_ptr(), ws.numel(), self._path_id(), stream))
         return out
 
+    @torch.no_grad()
+    def forward_u8(self, img_u8: torch.Tensor, mask_u8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """uint8 request path (scripts/demo.py:56-66 + :131-142 in one call): img_u8 [N,R,R,3] RGB and mask_u8 [N,R,R]
+        (255 = known) are HOST uint8 tensors (pinned for full speed); returns the composed uint8 image [N,R,R,3] on the
+        host: known pixels of img, generated pixels elsewhere.  Pre/post-processing run as CUDA kernels around the forward,
+        so 7 bytes per pixel cross PCIe instead of 28."""
+        r = self.resolution
+        if img_u8.is_cuda or mask_u8.is_cuda or img_u8.dtype != torch.uint8 or mask_u8.dtype != torch.uint8:
+            raise RuntimeError("forward_u8 expects CPU uint8 tensors")
+        if img_u8.dim() != 4 or tuple(img_u8.shape[1:]) != (r, r, 3) or tuple(mask_u8.shape) != (img_u8.shape[0], r, r):
+            raise RuntimeError("forward_u8 expects img [N, %d, %d, 3] and mask [N, %d, %d]" % (r, r, r, r))
+        img_u8, mask_u8 = img_u8.contiguous(), mask_u8.contiguous()
+        n = img_u8.shape[0]
+        if n == 0:
+            raise RuntimeError("empty batch")
+        device = next(self.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("module parameters must be on a CUDA device (call .to('cuda')); there is no CPU path")
+        if out is None:
+            out = torch.empty((n, r, r, 3), dtype=torch.uint8, pin_memory=True)
+        if out.is_cuda or out.dtype != torch.uint8 or tuple(out.shape) != (n, r, r, 3) or not out.is_contiguous():
+            raise RuntimeError("out must be a contiguous CPU uint8 tensor of shape [N, %d, %d, 3]" % (r, r))
+        with torch.cuda.device(device):
+            eng = self._engine(device)
+            nbytes = eng.lib.migan_workspace_bytes(eng.handle, n) + eng.lib.migan_u8_staging_bytes(eng.handle, n)
+            ws = eng.workspaces.get((n, "u8"))
+            if ws is None:
+                raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+                off = (-raw.data_ptr()) % 1024
+                ws = raw[off:off + nbytes]
+                eng.workspaces = {k: v for k, v in eng.workspaces.items() if k[0] == n}
+                eng.workspaces[(n, "u8")] = ws
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _abi.check(eng.lib.migan_forward_u8(eng.handle, img_u8.data_ptr(), mask_u8.data_ptr(), out.data_ptr(), n,
+                                                ws.data_ptr(), ws.numel(), self._path_id(), stream))
+        return out
+
     def host_wait(self) -> None:
         """Block until every batch enqueued with forward_host(wait=False) has landed in its output tensor."""
         for eng in self._engines.values():

@@ -244,3 +244,34 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     if up == 1 and down == 1 and [px0, px1, py0, py1] == [0, 0, 0, 0]:   # :145-147
         return _conv1x1(x, w)
     return _conv2d_resample_general(x, w, f, up, down, pad, groups, flip_weight, flip_filter)
+
+
+def preprocess_u8(img_u8: torch.Tensor, mask_u8: torch.Tensor) -> torch.Tensor:
+    """x[N,4,R,R] = cat([mask-0.5, img*mask]) from uint8 CUDA tensors img [N,R,R,3], mask [N,R,R] (255 = known):
+    scripts/demo.py:56-66, bit-exact with the torch expression there."""
+    if not (img_u8.is_cuda and mask_u8.is_cuda) or img_u8.dtype != torch.uint8 or mask_u8.dtype != torch.uint8:
+        raise RuntimeError("preprocess_u8 expects uint8 CUDA tensors: migan_b200.ops has no CPU path")
+    n, r = img_u8.shape[0], img_u8.shape[1]
+    if tuple(img_u8.shape) != (n, r, r, 3) or tuple(mask_u8.shape) != (n, r, r):
+        raise RuntimeError("preprocess_u8 expects img [N,R,R,3] and mask [N,R,R]")
+    img_u8, mask_u8 = img_u8.contiguous(), mask_u8.contiguous()
+    x = torch.empty((n, 4, r, r), dtype=torch.float32, device=img_u8.device)
+    with _guard(img_u8.device):
+        _abi.check(_abi.load().b200_preprocess_u8(img_u8.data_ptr(), mask_u8.data_ptr(), x.data_ptr(), n, r, _stream(img_u8)))
+    return x
+
+
+def postprocess_u8(y: torch.Tensor, img_u8: torch.Tensor, mask_u8: torch.Tensor) -> torch.Tensor:
+    """uint8 [N,R,R,3] composite of the generator output y [N,3,R,R] with the known pixels (scripts/demo.py:135-142)."""
+    y = _require_cuda_f32(y, "y")
+    n, r = y.shape[0], y.shape[2]
+    if tuple(y.shape) != (n, 3, r, r) or tuple(img_u8.shape) != (n, r, r, 3) or tuple(mask_u8.shape) != (n, r, r):
+        raise RuntimeError("postprocess_u8 expects y [N,3,R,R], img [N,R,R,3], mask [N,R,R]")
+    if not (img_u8.is_cuda and mask_u8.is_cuda) or img_u8.dtype != torch.uint8 or mask_u8.dtype != torch.uint8:
+        raise RuntimeError("postprocess_u8 expects uint8 CUDA tensors")
+    img_u8, mask_u8 = img_u8.contiguous(), mask_u8.contiguous()
+    out = torch.empty((n, r, r, 3), dtype=torch.uint8, device=y.device)
+    with _guard(y.device):
+        _abi.check(_abi.load().b200_postprocess_u8(y.data_ptr(), img_u8.data_ptr(), mask_u8.data_ptr(), out.data_ptr(), n, r,
+                                                   _stream(y)))
+    return out

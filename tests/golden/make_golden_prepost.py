@@ -1,0 +1,40 @@
+"""Pin oracle/prepost_oracle.preprocess against the reference's own scripts/demo.py:preprocess (build container only)."""
+import os
+import sys
+
+import numpy as np
+import torch
+from PIL import Image
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("MIGAN_REF", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from oracle import prepost_oracle as P  # noqa: E402
+
+
+def main():
+    from scripts.demo import preprocess as ref_preprocess
+    rng = np.random.RandomState(3)
+    for R in (64, 256):
+        img = rng.randint(0, 256, size=(R, R, 3), dtype=np.uint8)
+        mask = (rng.rand(R, R) > 0.4).astype(np.uint8) * 255
+        mask[0, :5] = [0, 1, 127, 254, 255]                     # only 255 counts as known (`// 255`)
+        x_ref = ref_preprocess(Image.fromarray(img), Image.fromarray(mask).convert("L"), R)
+        x_or = P.preprocess(img[None], mask[None])
+        assert x_ref.shape == x_or.shape and torch.equal(x_ref, x_or), R
+        print("preprocess R=%d pinned bit-exact" % R)
+    # post-processing vector (restatement only; see the oracle header)
+    g = torch.Generator().manual_seed(5)
+    y = torch.randn(2, 3, 32, 32, generator=g) * 1.5
+    y[0, 0, 0, :6] = torch.tensor([-1.0, 1.0, 0.0, 0.99999994, -1.0000001, 0.00392157 * 2 - 1])
+    img = rng.randint(0, 256, size=(2, 32, 32, 3), dtype=np.uint8)
+    mask = (rng.rand(2, 32, 32) > 0.5).astype(np.uint8) * 255
+    np.savez_compressed(os.path.join(HERE, "prepost.npz"), y=y.numpy(), img=img, mask=mask,
+                        x=P.preprocess(img, mask).numpy(), out=P.postprocess(y, img, mask))
+
+
+if __name__ == "__main__":
+    main()

@@ -314,3 +314,29 @@ def test_python_conv2d_resample_marshalling(emul_python):
         got = ops.conv2d_resample(x, w, f, up=up, down=down, padding=pad, groups=groups, flip_weight=flipw)
         assert tuple(got.shape) == tuple(want.shape)
         assert float((got - want).abs().max()) < 1e-4
+
+
+# ---- uint8 pre/post-processing kernels (prepost.cu) in the same emulation library ------------------------------------
+def test_prepost_u8_kernels_bit_exact(emul):
+    from oracle import prepost_oracle as P
+    lib = _abi.bind(emul, _abi.PREPOST_SYMBOLS)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "prepost.npz"))
+    img, mask, y = np.ascontiguousarray(gold["img"]), np.ascontiguousarray(gold["mask"]), np.ascontiguousarray(gold["y"])
+    n, r = img.shape[0], img.shape[1]
+    x = np.empty((n, 4, r, r), np.float32)
+    assert lib.b200_preprocess_u8(_ptr(img), _ptr(mask), _ptr(x), n, r, None) == 0
+    assert np.array_equal(x, gold["x"]) and np.array_equal(x, P.preprocess(img, mask).numpy())
+    out = np.empty((n, r, r, 3), np.uint8)
+    assert lib.b200_postprocess_u8(_ptr(y), _ptr(img), _ptr(mask), _ptr(out), n, r, None) == 0
+    assert np.array_equal(out, gold["out"]) and np.array_equal(out, P.postprocess(torch.from_numpy(y), img, mask))
+    # mask values other than 255 are holes (`// 255`), every uint8 image value
+    rng = np.random.RandomState(0)
+    img = np.ascontiguousarray(np.tile(np.arange(256, dtype=np.uint8)[None, :, None, None], (1, 1, 256, 3)))
+    mask = np.ascontiguousarray(rng.choice(np.array([0, 1, 128, 254, 255], np.uint8), size=(1, 256, 256)))
+    x = np.empty((1, 4, 256, 256), np.float32)
+    lib.b200_preprocess_u8(_ptr(img), _ptr(mask), _ptr(x), 1, 256, None)
+    assert np.array_equal(x, P.preprocess(img, mask).numpy())
+    y = (torch.linspace(-1.2, 1.2, 256 * 256 * 3).reshape(1, 3, 256, 256)).contiguous()
+    out = np.empty((1, 256, 256, 3), np.uint8)
+    lib.b200_postprocess_u8(_ptr(y.numpy()), _ptr(img), _ptr(mask), _ptr(out), 1, 256, None)
+    assert np.array_equal(out, P.postprocess(y, img, mask))

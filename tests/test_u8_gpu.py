@@ -1,0 +1,59 @@
+"""uint8 request path on the B200: the pre/post-processing kernels are bit-exact against the
+oracle restatement of scripts/demo.py:56-66 / :135-142; the fused host call equals kernel-by-kernel composition."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import migan_b200
+from migan_b200 import ops, synthetic
+from oracle import migan_oracle as O
+from oracle import prepost_oracle as P
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_prepost_kernels_bit_exact(cuda_device):
+    gold = np.load(os.path.join(GOLDEN, "prepost.npz"))
+    img, mask, y = torch.from_numpy(gold["img"]), torch.from_numpy(gold["mask"]), torch.from_numpy(gold["y"])
+    x = ops.preprocess_u8(img.to(cuda_device), mask.to(cuda_device)).cpu()
+    assert torch.equal(x, torch.from_numpy(gold["x"]))
+    out = ops.postprocess_u8(y.to(cuda_device), img.to(cuda_device), mask.to(cuda_device)).cpu()
+    assert torch.equal(out, torch.from_numpy(gold["out"]))
+    rng = np.random.RandomState(0)
+    img = torch.from_numpy(rng.randint(0, 256, size=(3, 128, 128, 3), dtype=np.uint8))
+    mask = torch.from_numpy(rng.choice(np.array([0, 1, 128, 254, 255], np.uint8), size=(3, 128, 128)))
+    x = ops.preprocess_u8(img.to(cuda_device), mask.to(cuda_device)).cpu()
+    assert torch.equal(x, P.preprocess(img.numpy(), mask.numpy()))
+    y = torch.linspace(-1.2, 1.2, 3 * 3 * 128 * 128).reshape(3, 3, 128, 128).contiguous()
+    out = ops.postprocess_u8(y.to(cuda_device), img.to(cuda_device), mask.to(cuda_device)).cpu()
+    assert np.array_equal(out.numpy(), P.postprocess(y, img.numpy(), mask.numpy()))
+
+
+@pytest.mark.parametrize("R,N", [(64, 3), (256, 2)])
+def test_forward_u8_equals_composition(cuda_device, R, N):
+    model = migan_b200.Generator(R)
+    sd = O.make_state_dict(R, seed=1)
+    model.load_state_dict(sd)
+    model = model.to(cuda_device).eval()
+    rng = np.random.RandomState(R)
+    img = torch.from_numpy(rng.randint(0, 256, size=(N, R, R, 3), dtype=np.uint8))
+    mask = torch.from_numpy(((rng.rand(N, R, R) > 0.4) * 255).astype(np.uint8))
+    out = model.forward_u8(img.pin_memory(), mask.pin_memory())
+    assert out.shape == (N, R, R, 3) and out.dtype == torch.uint8 and not out.is_cuda
+    # (a) same kernels, called one by one on the device: identical
+    x = ops.preprocess_u8(img.to(cuda_device), mask.to(cuda_device))
+    step = ops.postprocess_u8(model(x), img.to(cuda_device), mask.to(cuda_device)).cpu()
+    assert torch.equal(out, step)
+    # (b) against the CPU oracle chain: the generator output differs by ~1e-5, so a value sitting on a uint8 boundary may
+    # truncate to the neighbouring level; known pixels are copied and must be identical.
+    y_or = O.generator_forward(sd, P.preprocess(img.numpy(), mask.numpy()), R)
+    want = torch.from_numpy(P.postprocess(y_or, img.numpy(), mask.numpy()))
+    diff = (out.int() - want.int()).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-3
+    known = (mask == 255)
+    assert torch.equal(out[known], img[known])
+    with pytest.raises(RuntimeError):
+        model.forward_u8(img.float(), mask)
