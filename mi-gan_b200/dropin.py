@@ -25,6 +25,13 @@ def install() -> None:
     ref_mod = importlib.import_module("lib.model_zoo.migan_inference")
     ref_mod.ReferenceGenerator = ref_mod.Generator   # keep the original reachable for A/B comparisons
     ref_mod.Generator = migan_b200.Generator
+    # Co-Mod-GAN (scripts/demo.py:16-21 imports Generator / Mapping / Encoder / Synthesis from lib.model_zoo.comodgan)
+    from migan_b200 import comodgan
+
+    ref_cm = importlib.import_module("lib.model_zoo.comodgan")
+    for name in ("Generator", "Mapping", "Encoder", "Synthesis"):
+        setattr(ref_cm, "Reference" + name, getattr(ref_cm, name))
+        setattr(ref_cm, name, getattr(comodgan, name))
 
 
 def main(argv=None) -> None:

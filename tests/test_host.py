@@ -146,3 +146,27 @@ def test_comodgan_constructor_and_cpu_errors(lib):
     assert lib.comodgan_create(16, -1, ctypes.byref(h)) == 0
     assert lib.comodgan_finalize_weights(h) != 0        # no device, no weights: fails loudly
     lib.comodgan_destroy(h)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/lib/model_zoo"), reason="reference checkout not present (GPU box)")
+def test_dropin_rebinds_reference_modules(lib, monkeypatch):
+    """python -m migan_b200.dropin scripts.demo ...: the reference's import sites (scripts/demo.py:15-21) resolve to the
+    B200 classes without editing any reference file.  Build container only."""
+    import importlib
+    import warnings
+    monkeypatch.syspath_prepend("/root/reference")
+    warnings.filterwarnings("ignore")
+    from migan_b200 import comodgan, dropin
+    ref_mi = importlib.import_module("lib.model_zoo.migan_inference")
+    ref_cm = importlib.import_module("lib.model_zoo.comodgan")
+    saved = (ref_mi.Generator, ref_cm.Generator, ref_cm.Mapping, ref_cm.Encoder, ref_cm.Synthesis)
+    try:
+        dropin.install()
+        assert ref_mi.Generator is migan_b200.Generator and ref_mi.ReferenceGenerator is saved[0]
+        assert ref_cm.Generator is comodgan.Generator and ref_cm.ReferenceGenerator is saved[1]
+        # the construction of scripts/demo.py:95-100, through the patched names
+        model = ref_cm.Generator(ref_cm.Mapping(num_ws=14), ref_cm.Encoder(resolution=256), ref_cm.Synthesis(resolution=256))
+        ref_keys = list(saved[1](saved[2](num_ws=14), saved[3](resolution=256), saved[4](resolution=256)).state_dict().keys())
+        assert list(model.state_dict().keys()) == ref_keys
+    finally:
+        ref_mi.Generator, ref_cm.Generator, ref_cm.Mapping, ref_cm.Encoder, ref_cm.Synthesis = saved
