@@ -130,6 +130,10 @@ class Generator(nn.Module):
         for m in self.modules():
             if hasattr(m, "conv1") and hasattr(m, "conv2") and hasattr(m.conv2, "weight") and hasattr(m.conv1, "bias"):
                 m.use_noise = hasattr(m, "noise_const")
+                m.conv2.register_parameter("bias", None)      # nn.Conv2d(..., bias=False) of migan_inference.py:136
+        for blk in self.encoder.children():                   # EncoderBlock.fromrgb is None except in the first block (:176-186)
+            if not hasattr(blk, "fromrgb"):
+                blk.fromrgb = None
         self._engines: Dict[torch.device, _Engine] = {}
 
     def __getstate__(self):  # engines hold C handles: never pickled / deep-copied

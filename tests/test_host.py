@@ -170,3 +170,40 @@ def test_dropin_rebinds_reference_modules(lib, monkeypatch):
         assert list(model.state_dict().keys()) == ref_keys
     finally:
         ref_mi.Generator, ref_cm.Generator, ref_cm.Mapping, ref_cm.Encoder, ref_cm.Synthesis = saved
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/lib/model_zoo"), reason="reference checkout not present (GPU box)")
+def test_reference_export_script_accepts_b200_generator(lib, monkeypatch):
+    """scripts/export_inference_model.py:17-85 `copy_weights(source_G, dest)` -- the reference's route from a training
+    snapshot (re-parameterised train graph, lib/model_zoo/migan.py) to inference weights -- works with the B200 class as
+    `dest` (attribute paths, `fromrgb is None`, `conv2.bias is None`, `use_noise`), and gives the same state_dict as with
+    the reference's own inference Generator.  Also the reference's behavioural pin: train graph == inference graph
+    (export_inference_model.py:149-151), here against the oracle.  Build container only."""
+    import importlib
+    import warnings
+    monkeypatch.syspath_prepend("/root/reference")
+    warnings.filterwarnings("ignore")
+    M = importlib.import_module("lib.model_zoo.migan")
+    ref_inf = importlib.import_module("lib.model_zoo.migan_inference")
+    exp = importlib.import_module("scripts.export_inference_model")
+    R = 64
+    torch.manual_seed(0)
+    src = M.Generator(M.Encoder(resolution=R, ic_n=4, depthwise=True, reparametrize=True, num_reparam_tensors=9),
+                      M.Synthesis(resolution=R, depthwise=True, reparametrize=True, num_reparam_tensors=9)).eval()
+    with torch.no_grad():
+        for name, p in src.named_parameters():
+            if name.endswith("bias"):
+                p.copy_(0.2 * torch.randn_like(p))
+            if name.endswith("noise_strength"):
+                p.fill_(0.3)
+    ref, mine = ref_inf.Generator(resolution=R).eval(), migan_b200.Generator(R).eval()
+    exp.copy_weights(src, ref, resolution=R)
+    exp.copy_weights(src, mine, resolution=R)
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    x = O.make_input(R, 2)
+    with torch.no_grad():
+        y_src = src(x, noise_mode="const")
+    y_or = O.generator_forward({k: v.detach() for k, v in b.items()}, x, R)
+    assert float((y_src - y_or).abs().max()) < 1e-4            # SURVEY 8c pin (1): 1.05e-5 at output scale 13.6
