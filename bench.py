@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--res", type=int, default=None, help="default 512 (migan) / 256 (comodgan)")
     ap.add_argument("--batch", type=int, default=None, help="images per GPU; default 32 (migan) / 16 (comodgan)")
     ap.add_argument("--path", default=os.environ.get("MIGAN_B200_PATH", "tc"))
+    ap.add_argument("--comod-gemm", default=None, choices=["simt", "tc"],
+                    help="comodgan workload: GEMM engine (tc = staged tcgen05 route, not yet run on hardware)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-launch table (JSON) here")
     args = ap.parse_args()
@@ -406,6 +408,8 @@ def run_comodgan(args):
     CUDA-core GEMMs (no tensor cores yet), so the roofline fraction against the tensor peak is small by construction."""
     from migan_b200 import comodgan
 
+    if args.comod_gemm:
+        os.environ["COMOD_GEMM"] = args.comod_gemm
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -477,7 +481,8 @@ def run_comodgan(args):
         "warmup": Wm, "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "comodgan-%d Generator.forward (z given, noise_mode=const), %d images/GPU" % (R, B),
-                   "arithmetic": "exact fp32: im2col + CUDA-core GEMM (round-1 first path; tcgen05 implicit GEMM is the next step)",
+                   "arithmetic": "exact fp32: im2col + CUDA-core GEMM (round-1 first path; tcgen05 implicit GEMM is the next step)"
+                   if os.environ.get("COMOD_GEMM") != "tc" else "im2col fp16 hi/lo split + tcgen05 3-pass GEMM (staged route)",
                    "global_batch": world * B, "weights": "constructor-style N(0,1) + non-zero biases / noise strengths",
                    "l2": "col matrices are GBs per layer: far beyond the 126 MB L2"},
         "roofline": {"bound": "tensor", "kernel": "pw_gemm_simt (all GEMM launches)", "achieved": achieved, "peak": tpeak,

@@ -24,9 +24,21 @@ typedef void* ck_stream_t;
 typedef cudaStream_t ck_stream_t;
 #endif
 
+#ifdef MIGAN_EMULATE
+typedef _Float16 ck_half;                       // IEEE binary16, round-to-nearest-even conversions (GCC, x86-64)
+CK_HD ck_half ck_f2h(float v) { return (ck_half)v; }
+CK_HD float ck_h2f(ck_half h) { return (float)h; }
+#else
+#include <cuda_fp16.h>
+typedef __half ck_half;
+CK_HD ck_half ck_f2h(float v) { return __float2half_rn(v); }
+CK_HD float ck_h2f(ck_half h) { return __half2float(h); }
+#endif
+
 namespace comod {
 
 struct alignas(16) f4 { float x, y, z, w; };
+struct alignas(8) h4 { ck_half x, y, z, w; };
 CK_HD f4 ld4(const float* p) { return *reinterpret_cast<const f4*>(p); }
 CK_HD void st4(float* p, const f4& v) { *reinterpret_cast<f4*>(p) = v; }
 
@@ -116,6 +128,37 @@ struct Im2col4K {      // items = P*KP/4 (one float4 each); needs Cg, c0, Ct mul
             }
         }
         st4(out + p * KP + k, v);
+    }
+};
+
+// Same gather, written as the fp16 hi / lo pair of v * a_scale (v*a_scale ~= hi + lo, 22 significant bits): the A operand
+// of the tcgen05 GEMM (sepconv_tc.cu, A_TMA mode), K-major rows of KP halves (KP a multiple of 64).
+struct Im2colSplit4K { // items = P*KP/4; needs Cg, c0, Ct multiples of 4
+    const float* in; const float* scale; ck_half* hi; ck_half* lo; float a_scale;
+    int H, W, Ct, c0, Cg, kh, kw, stride, pad_y, pad_x, OH, OW, KP;
+    CK_HD void operator()(int64_t i) const {
+        const int kq = KP >> 2;
+        const int k = (int)(i % kq) * 4; const int64_t p = i / kq;
+        const int ox = (int)(p % OW); const int64_t t = p / OW;
+        const int oy = (int)(t % OH); const int64_t n = t / OH;
+        f4 v = {0.f, 0.f, 0.f, 0.f};
+        if (k < kh * kw * Cg) {
+            const int tap = k / Cg, c = k - tap * Cg;
+            const int ky = tap / kw, kx = tap - ky * kw;
+            const int iy = oy * stride + ky - pad_y, ix = ox * stride + kx - pad_x;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                v = ld4(in + ((n * H + iy) * (int64_t)W + ix) * Ct + c0 + c);
+                if (scale) {
+                    const f4 s = ld4(scale + n * Cg + c);
+                    v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+                }
+            }
+        }
+        v.x *= a_scale; v.y *= a_scale; v.z *= a_scale; v.w *= a_scale;
+        h4 h = {ck_f2h(v.x), ck_f2h(v.y), ck_f2h(v.z), ck_f2h(v.w)};
+        h4 l = {ck_f2h(v.x - ck_h2f(h.x)), ck_f2h(v.y - ck_h2f(h.y)), ck_f2h(v.z - ck_h2f(h.z)), ck_f2h(v.w - ck_h2f(h.w))};
+        *reinterpret_cast<h4*>(hi + p * KP + k) = h;
+        *reinterpret_cast<h4*>(lo + p * KP + k) = l;
     }
 };
 

@@ -33,6 +33,7 @@
 
 #ifndef MIGAN_EMULATE
 #include "kernels.h"
+#include "sepconv_tc.h"
 #endif
 
 namespace {
@@ -79,6 +80,25 @@ int gemm_f32(const float* A, const float* Bt, float* out, int64_t P, int K, int 
     }
     return 0;
 }
+// Emulation of the tcgen05 3-pass GEMM (sepconv_tc.cu, A_TMA mode): out = inv_scale * (Ah*Bh + Ah*Bl + Al*Bh), K-major operands.
+const char* gemm_tc(const ck_half* a_hi, const ck_half* a_lo, const ck_half* b_hi, const ck_half* b_lo, float inv_scale,
+                    float* out, int n, int res, int K, int N, ck_stream_t) {
+    const int64_t P = (int64_t)n * res * res;
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < P; ++p)
+        for (int j = 0; j < N; ++j) {
+            float acc = 0.f, corr = 0.f;
+            for (int k = 0; k < K; ++k) {
+                const float ah = ck_h2f(a_hi[p * K + k]), al = ck_h2f(a_lo[p * K + k]);
+                const float bh = ck_h2f(b_hi[(int64_t)j * K + k]), bl = ck_h2f(b_lo[(int64_t)j * K + k]);
+                acc += ah * bh;
+                corr += ah * bl + al * bh;
+            }
+            out[p * N + j] = (acc + corr) * inv_scale;
+        }
+    return nullptr;
+}
+int tc_configure() { return 0; }
 #else
 int dev_set(int d) { return (int)cudaSetDevice(d); }
 int dev_alloc(void** p, size_t bytes) { return (int)cudaMalloc(p, std::max<size_t>(bytes, 256)); }
@@ -89,6 +109,18 @@ const char* dev_err(int e) { return cudaGetErrorString((cudaError_t)e); }
 int gemm_f32(const float* A, const float* Bt, float* out, int64_t P, int K, int N, ck_stream_t s) {
     return (int)migan::launch_pw_gemm_simt(A, Bt, out, P, K, N, nullptr, 1, 0, s);
 }
+// The tcgen05 kernel of the MI-GAN path in its plain-GEMM configuration (pre-split A operand by TMA, no activation):
+// out[n][res][res][N] = inv_scale * A[P][K] * B[N][K]^T with the fp16 hi/lo 3-pass split, fp32 accumulation in TMEM.
+const char* gemm_tc(const ck_half* a_hi, const ck_half* a_lo, const ck_half* b_hi, const ck_half* b_lo, float inv_scale,
+                    float* out, int n, int res, int K, int N, ck_stream_t s) {
+    migan::SepconvTcArgs args;
+    if (const char* err = migan::sepconv_tc_plan(&args, 3, nullptr, a_hi, a_lo, nullptr, nullptr, b_hi, b_lo, inv_scale, nullptr,
+                                                 out, n, res, K, N, 0, nullptr))
+        return err;
+    const cudaError_t e = migan::launch_sepconv_tc(args, s);
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+int tc_configure() { return (int)migan::configure_sepconv_tc(); }
 #endif
 
 // ---- workspace walker ----------------------------------------------------------------------------------------------
@@ -122,6 +154,17 @@ struct Runner {
         const int e = gemm_f32(A, Bt, out, P, K, N, s);
         if (e) rc = fail(ERR_CUDA, "GEMM launch failed: %s", dev_err(e));
         ++launches;
+    }
+    void gemm_tc_(const ck_half* a_hi, const ck_half* a_lo, const ck_half* b_hi, const ck_half* b_lo, float inv_scale, float* out,
+                  int n, int res, int K, int N) {
+        if (dry || rc || n <= 0) return;
+        if (const char* err = gemm_tc(a_hi, a_lo, b_hi, b_lo, inv_scale, out, n, res, K, N, s)) rc = fail(ERR_CUDA, "tcgen05 GEMM: %s", err);
+        ++launches;
+    }
+    void im2col_split(const float* in, const float* scale, ck_half* hi, ck_half* lo, float a_scale, int64_t n, int H, int W, int C,
+                      int kh, int kw, int stride, int pad_y, int pad_x, int OH, int OW, int KP) {
+        Im2colSplit4K k{in, scale, hi, lo, a_scale, H, W, C, 0, C, kh, kw, stride, pad_y, pad_x, OH, OW, KP};
+        launch(k, n * OH * OW * (KP / 4));
     }
     // NHWC upfirdn2d; taps already flipped * gain.
     void fir(const float* in, float* out, const float* add, int64_t n, int H, int W, int C, const float* taps, int fh, int fw,
@@ -168,6 +211,11 @@ struct ConvL {
     int ws_index = 0;
     int KP = 0, NP = 0;
     float* Bt = nullptr;     // plain: [KP][NP] ; up: [round16(cin)][round64(k*k*cout)]
+    // tcgen05 route (COMOD_GEMM=tc, up == 1 layers): K-major fp16 hi/lo of w * 2^k, [NPc][KPc], KPc = round64(k*k*cin)
+    ck_half* Bh = nullptr;
+    ck_half* Bl = nullptr;
+    int KPc = 0, NPc = 0;
+    float tc_inv_scale = 1.f;
     float* bias = nullptr;   // [cout] or null
     float* wsq = nullptr;    // [cin][cout] sum over taps of the pre-normalised weight squared (demod)
     DenseL affine;           // [1536] -> [cin]
@@ -210,9 +258,12 @@ struct comodgan_ctx {
     float* tap_dst = nullptr;
     int last_launches = 0;
     size_t col_cap_floats = (size_t)512 << 20;
+    bool use_tc = false;     // COMOD_GEMM=tc: k x k / 1x1 convolutions (not the transposed ones, not the dense layers) on tcgen05
 };
 
 namespace {
+
+constexpr float kTcActScale = 8.f;   // A-operand scale of the fp16 split: |x * style| <= 8188 stays finite in fp16
 
 void add_spec(comodgan_ctx* c, const std::string& name, std::initializer_list<int64_t> shape) {
     Spec s;
@@ -376,6 +427,42 @@ int pack_conv(comodgan_ctx* c, ConvL& L, const std::string& p, int cin, int cout
     if (e) return fail(ERR_CUDA, "weight packing failed: %s", dev_err(e));
     c->allocs.push_back(bt);
     L.Bt = (float*)bt;
+    if (c->use_tc && up == 1 && cin % 4 == 0) {
+        // B[o][k], k = (ky*kw + kx)*cin + ci: same values as the fp32 operand, K-major, scaled by a power of two so that the
+        // largest weight lands in [8192, 16384) (both halves well inside fp16's normal range), split into hi + lo.
+        L.KPc = round_up(taps * cin, 64);
+        L.NPc = round_up(cout, 64);
+        std::vector<float> b((size_t)L.NPc * L.KPc, 0.f);
+        float maxabs = 0.f;
+        for (int o = 0; o < cout; ++o)
+            for (int t = 0; t < taps; ++t) {
+                const int ts = flip_weight ? t : taps - 1 - t;          // mirrored taps = true convolution
+                for (int ci = 0; ci < cin; ++ci) {
+                    const float v = w[((size_t)o * cin + ci) * taps + ts] * gain * oscale[o];
+                    b[(size_t)o * L.KPc + t * cin + ci] = v;
+                    if (std::isfinite(v)) maxabs = std::max(maxabs, std::fabs(v));
+                }
+            }
+        int k2 = maxabs > 0.f ? (int)std::floor(std::log2(16384.0 / (double)maxabs)) : 0;
+        k2 = std::max(-14, std::min(24, k2));
+        const float wscale = std::ldexp(1.0f, k2);
+        L.tc_inv_scale = 1.0f / (wscale * kTcActScale);
+        std::vector<ck_half> hi(b.size()), lo(b.size());
+        for (size_t i = 0; i < b.size(); ++i) {
+            const float sv = b[i] * wscale;
+            hi[i] = ck_f2h(sv);
+            lo[i] = ck_f2h(sv - ck_h2f(hi[i]));
+        }
+        void* d[2] = {nullptr, nullptr};
+        for (int j = 0; j < 2; ++j) {
+            if (int e2 = dev_alloc(&d[j], b.size() * sizeof(ck_half))) return fail(ERR_CUDA, "device allocation failed: %s", dev_err(e2));
+            c->allocs.push_back(d[j]);
+            dev_copy(d[j], j == 0 ? (const void*)hi.data() : (const void*)lo.data(), b.size() * sizeof(ck_half), nullptr);
+        }
+        if (int e2 = dev_sync()) return fail(ERR_CUDA, "weight upload failed: %s", dev_err(e2));
+        L.Bh = (ck_half*)d[0];
+        L.Bl = (ck_half*)d[1];
+    }
     if (c->index.count(p + ".bias")) {
         if (int rc = upload(c, H(c, p + ".bias"), &L.bias)) return rc;
     }
@@ -459,8 +546,14 @@ struct Walk {
         const bool g_sep = (L.up == 1) && L.NP != cout;              // GEMM output needs its own buffer
         const int Hf = Hin + 1;                                       // FIR-padded input of the down path
         const int Ht = (Hin - 1) * L.up + L.k;                        // conv_transpose2d output (padding 0)
+        const bool tc = c->use_tc && L.up == 1 && L.Bh != nullptr;   // tcgen05 route (staged, off by default)
+        const bool g_sep_tc = tc && L.NPc != cout;
         size_t per_img = 0;
-        if (L.up == 1) {
+        if (tc) {
+            if (L.down > 1) per_img += (size_t)Hf * Hf * cin;
+            per_img += (size_t)HWo * L.KPc;                           // hi + lo halves = KPc floats per pixel
+            if (g_sep_tc) per_img += (size_t)HWo * L.NPc;
+        } else if (L.up == 1) {
             if (L.down > 1) per_img += (size_t)Hf * Hf * cin;
             if (!direct_a) per_img += (size_t)HWo * L.KP;
             if (g_sep) per_img += (size_t)HWo * L.NP;
@@ -471,7 +564,13 @@ struct Walk {
         int64_t chunk = per_img ? (int64_t)(R.col_cap_floats / per_img) : n;
         chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, n));
         float *F = nullptr, *col = nullptr, *G = nullptr, *T = nullptr;
-        if (L.up == 1) {
+        ck_half *ch = nullptr, *cl = nullptr;
+        if (tc) {
+            if (L.down > 1) F = R.take((size_t)chunk * Hf * Hf * cin);
+            ch = reinterpret_cast<ck_half*>(R.take((size_t)chunk * HWo * L.KPc / 2));
+            cl = reinterpret_cast<ck_half*>(R.take((size_t)chunk * HWo * L.KPc / 2));
+            if (g_sep_tc) G = R.take((size_t)chunk * HWo * L.NPc);
+        } else if (L.up == 1) {
             if (L.down > 1) F = R.take((size_t)chunk * Hf * Hf * cin);
             if (!direct_a) col = R.take((size_t)chunk * HWo * L.KP);
             if (g_sep) G = R.take((size_t)chunk * HWo * L.NP);
@@ -498,14 +597,21 @@ struct Walk {
                     R.fir(in_c, F, nullptr, cnt, Hin, Hin, cin, L.fir, 4, 4, 1, 1, p0, p0, Hf, Hf);
                     src = F; Hs = Hf; stride = L.down; pad = 0;
                 }
-                const float* A = src;
-                if (!direct_a) {
-                    R.im2col(src, scale_c, col, cnt, Hs, Hs, cin, 0, cin, L.k, L.k, stride, pad, pad, Hout, Hout, L.KP);
-                    A = col;
+                if (tc) {
+                    R.im2col_split(src, scale_c, ch, cl, kTcActScale, cnt, Hs, Hs, cin, L.k, L.k, stride, pad, pad, Hout, Hout, L.KPc);
+                    float* gout = g_sep_tc ? G : out_c;
+                    R.gemm_tc_(ch, cl, L.Bh, L.Bl, L.tc_inv_scale, gout, (int)cnt, Hout, L.KPc, L.NPc);
+                    g_src = gout; g_np = L.NPc;
+                } else {
+                    const float* A = src;
+                    if (!direct_a) {
+                        R.im2col(src, scale_c, col, cnt, Hs, Hs, cin, 0, cin, L.k, L.k, stride, pad, pad, Hout, Hout, L.KP);
+                        A = col;
+                    }
+                    float* gout = g_sep ? G : out_c;
+                    R.gemm(A, L.Bt, gout, cnt * HWo, L.KP, L.NP);
+                    g_src = gout; g_np = L.NP;
                 }
-                float* gout = g_sep ? G : out_c;
-                R.gemm(A, L.Bt, gout, cnt * HWo, L.KP, L.NP);
-                g_src = gout; g_np = L.NP;
             } else {
                 // conv2d_resample.py:94-98,124-142 with k=3, up=2, padding=1, 4x4 filter: px0 = 1+2-2 = 1, px1 = 1+1-1 = 1,
                 // pxt = 0: conv_transpose2d(stride 2, padding 0) then upfirdn2d(pad 1,1,1,1, gain 4).
@@ -623,6 +729,10 @@ int comodgan_create(int resolution, int device, comodgan_ctx** out) {
     c->host.resize(c->specs.size());
     c->have.assign(c->specs.size(), false);
     if (const char* e = getenv("COMOD_COL_CAP_MB")) c->col_cap_floats = (size_t)std::max(1, atoi(e)) * (1 << 20) / 4;
+    if (const char* e = getenv("COMOD_GEMM")) c->use_tc = (strcmp(e, "tc") == 0);
+    if (c->use_tc && device >= 0) {
+        if (int e2 = tc_configure()) { delete c; return fail(ERR_CUDA, "tcgen05 kernel setup failed: %s", dev_err(e2)); }
+    }
     *out = c;
     return 0;
 }

@@ -340,3 +340,20 @@ def test_prepost_u8_kernels_bit_exact(emul):
     out = np.empty((1, 256, 256, 3), np.uint8)
     lib.b200_postprocess_u8(_ptr(y.numpy()), _ptr(img), _ptr(mask), _ptr(out), 1, 256, None)
     assert np.array_equal(out, P.postprocess(y, img, mask))
+
+
+def test_staged_tcgen05_route_operands(emul, monkeypatch):
+    """COMOD_GEMM=tc (off by default, staged for round 2): plain / strided / 1x1 convolutions feed the tcgen05 GEMM of the
+    MI-GAN path (sepconv_tc.cu, A_TMA mode) with an fp16 hi/lo split im2col and K-major hi/lo weights.  The emulation
+    replaces only that GEMM by its arithmetic (Ah*Bh + Ah*Bl + Al*Bh, fp32 accumulate); the operand packing, scales,
+    K/N padding and chunking around it are the product code.  Not yet run on hardware."""
+    monkeypatch.setenv("COMOD_GEMM", "tc")
+    monkeypatch.setenv("COMOD_COL_CAP_MB", "2")
+    sd = C.make_state_dict(16, seed=1)
+    g = EmulGen(emul, 16, sd)
+    x, z = O.make_input(16, 2, seed=1234), C.make_latent(2, seed=1235)
+    y = g(x, z, psi=0.8, cutoff=2)
+    y_or = C.generator_forward(sd, x, z, 16, truncation_psi=0.8, truncation_cutoff=2)
+    err = float((y - y_or).abs().max())
+    assert err < 1e-3, err
+    g.close()
