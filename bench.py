@@ -375,7 +375,8 @@ def run_b200(args):
                    "l2": "per-step working set (input 134 MB + ~10 GB of activations at 512/32) exceeds the 126 MB L2; no flush needed",
                    "kernel_timing": "separate pass of K steps with cudaEvents around every launch",
                    "e2e": "K host batches submitted back to back through migan_forward_host_async (pinned H2D + forward + D2H "
-                          "per batch, two staging slots, two micro-batches), timed until the last output landed in host memory"},
+                          "per batch, two staging slots so the copies of batch t+1 / t-1 run under the kernels of batch t), timed until the last "
+                          "output landed in host memory"},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8,
         "gpu_launches": launches_per_step * K,
     }

@@ -80,7 +80,7 @@ size_t migan_host_staging_bytes(const migan_ctx* ctx, int n);
 int migan_forward_host(migan_ctx* ctx, const float* x_host, float* y_host, int n,
                        void* workspace, size_t workspace_bytes, int path, void* stream);
 /* Serving form: enqueue only.  Consecutive calls alternate between the two staging slots, so the copies of
- * batch t+1 overlap the kernels and the copy-out of batch t; migan_host_wait() blocks until every enqueued
+ * batch t+1 overlap the kernels and the copy-out of batch t (the batch is not split here: the overlap is across calls); migan_host_wait() blocks until every enqueued
  * batch has landed in its y_host.  x_host / y_host must stay valid (and unmodified) until then. */
 int migan_forward_host_async(migan_ctx* ctx, const float* x_host, float* y_host, int n,
                              void* workspace, size_t workspace_bytes, int path, void* stream);

@@ -869,7 +869,11 @@ static int forward_host_enqueue(migan_ctx* ctx, const float* x_host, float* y_ho
     CUDA_TRY(cudaSetDevice(ctx->device));
     // Micro-batch pipeline: H2D of micro-batch k+1 and D2H of k-1 overlap the kernels of k (three streams).
     // The small-resolution layers cost a fixed ~0.4 ms per forward, so the split is kept coarse.
-    int M = (n >= 8 && n % 2 == 0) ? 2 : 1;   // measured at 512x512, n = 32: M = 1 / 2 / 4 / 8 -> 1770 / 1926 / 1896 / 1678 img/s
+    // Synchronous call (one batch, then wait): split it so the copies of one half overlap the kernels of the other
+    // (measured at 512x512, n = 32: M = 1 / 2 / 4 / 8 -> 1770 / 1926 / 1896 / 1678 img/s).  Enqueue-only call: consecutive
+    // batches already overlap through the two staging slots (H2D of batch t+1 and D2H of batch t-1 run under the kernels of
+    // batch t), so the batch stays whole and does not pay the fixed per-forward cost of the small layers twice.
+    int M = (slot_out != nullptr && n >= 8 && n % 2 == 0) ? 2 : 1;
     if (const char* e = getenv("MIGAN_HOST_PIPELINE")) {
         const int v = atoi(e);
         if (v >= 1 && n % v == 0) M = v;
