@@ -895,9 +895,12 @@ static int forward_host_enqueue(migan_ctx* ctx, const float* x_host, float* y_ho
     cudaEvent_t ev_start = ev[2 * M];
     const int m = n / M;
     const size_t xs = (size_t)m * 4 * ctx->resolution * ctx->resolution, ys = (size_t)m * 3 * ctx->resolution * ctx->resolution;
-    CUDA_TRY(cudaEventRecord(ev_start, st));                  // order after whatever the caller queued on `stream`
-    CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ev_start, 0));
-    CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ev_start, 0));
+    // The copy-in stream does NOT wait for the caller's stream: x_host is host memory (valid from the call on) and the
+    // only device hazard -- the staging slot still being read by the forward that used it two calls ago -- is covered by
+    // slot_compute_done below.  Waiting on `stream` here would serialise the H2D of batch t+1 behind the kernels of
+    // batch t, which is exactly the overlap the two slots exist for.  The copy-out stream only ever waits for the
+    // compute-done events recorded after this point.
+    (void)ev_start;
     if (ctx->slot_used[slot]) {
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->slot_compute_done[slot], 0));   // xd[slot] free again
         CUDA_TRY(cudaStreamWaitEvent(st, ctx->slot_out_done[slot], 0));              // yd[slot] copied out
