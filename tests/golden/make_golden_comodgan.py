@@ -81,6 +81,17 @@ def main():
             x_checksum=checksum(x), z_checksum=checksum(z), w_checksum=sum(checksum(v) for v in sd.values()),
             fp64_maxabs=f64err, tap_names=np.array(names), tap_stats=stats)
 
+    # comodgan-512 (scripts/demo.py:101-106, num_ws=16): pin only, no fixture (3 MB)
+    ref = build_reference(512)
+    sd = C.make_state_dict(512, seed=2)
+    ref.load_state_dict(sd, strict=True)
+    x, z = O.make_input(512, 1, seed=3), C.make_latent(1, seed=4)
+    with torch.no_grad():
+        y_ref = ref(x.clone(), z=z.clone(), noise_mode="const")
+    err = float((y_ref - C.generator_forward(sd, x, z, 512)).abs().max())
+    print("R=512 N=1  ref-vs-oracle max-abs = %.3e" % err)
+    assert err == 0.0
+
     # conv2d_resample: every branch, against the reference op (impl falls back to its own ref path on CPU) -------
     g = torch.Generator().manual_seed(11)
     f = ref_upfirdn2d.setup_filter([1, 3, 3, 1])

@@ -152,3 +152,16 @@ def test_conv2d_resample_odd_shapes(cuda_device):
                                   down=down, padding=pad, groups=groups, flip_weight=flipw, flip_filter=flipf)
         assert tuple(got.shape) == tuple(want.shape)
         assert float((got.cpu() - want).abs().max()) < 1e-4
+
+
+def test_comodgan_512_matches_oracle(cuda_device):
+    """scripts/demo.py:101-106 (comodgan-512, num_ws=16): adds the 64-channel levels.  The oracle is pinned bit-exact to
+    the reference at this size by make_golden_comodgan.py (no fixture committed: 3 MB)."""
+    sd = C.make_state_dict(512, seed=2)
+    g = make_generator(512, sd, cuda_device)
+    assert g.num_ws == 16
+    x, z = O.make_input(512, 1, seed=3), C.make_latent(1, seed=4)
+    y = g(x.to(cuda_device), z=z.to(cuda_device), noise_mode="const").cpu()
+    err = (y - C.generator_forward(sd, x, z, 512)).abs()
+    print("comodgan-512 n=1: max-abs %.3e mean-abs %.3e" % (float(err.max()), float(err.mean())))
+    assert float(err.max()) < TOL
