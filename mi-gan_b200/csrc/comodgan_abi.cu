@@ -904,8 +904,10 @@ int b200_conv2d_resample(const float* x, const float* w, const float* f, float* 
         for (int i = 0; i < fh * fw; ++i) out[i] = (flip_filter ? taps_raw[i] : taps_raw[fh * fw - 1 - i]) * gain;
     };
     // conv2d_resample.py:94-103
-    if (up > 1) { px0 += (fw + up - 1) / 2; px1 += (fw - up) / 2; py0 += (fh + up - 1) / 2; py1 += (fh - up) / 2; }
-    if (down > 1) { px0 += (fw - down + 1) / 2; px1 += (fw - down) / 2; py0 += (fh - down + 1) / 2; py1 += (fh - down) / 2; }
+    // Python's // floors: (fw - up) is negative for filters shorter than the factor (f = None: fw = 1)
+    auto fdiv2 = [](int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); };
+    if (up > 1) { px0 += fdiv2(fw + up - 1); px1 += fdiv2(fw - up); py0 += fdiv2(fh + up - 1); py1 += fdiv2(fh - up); }
+    if (down > 1) { px0 += fdiv2(fw - down + 1); px1 += fdiv2(fw - down); py0 += fdiv2(fh - down + 1); py1 += fdiv2(fh - down); }
 
     const int cin_g = cin / groups, cout_g = cout / groups;
     for (int pass = 0; pass < 2; ++pass) {

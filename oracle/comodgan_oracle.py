@@ -163,7 +163,8 @@ def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_w
 def conv2d_resample_ref(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
     """conv2d_resample.py:59-154, all six branches."""
     out_channels, in_channels_per_group, kh, kw = w.shape
-    fw = fh = 1 if f is None else int(f.shape[-1])
+    fw = 1 if f is None else int(f.shape[-1])          # _get_filter_size (conv2d_resample.py:... upfirdn2d.py:47-57)
+    fh = 1 if f is None else int(f.shape[0])
     if isinstance(padding, int):
         padding = [padding] * 4
     elif len(padding) == 2:

@@ -112,6 +112,25 @@ def main():
         out[name + ".x"], out[name + ".w"], out[name + ".y"] = x.numpy(), w.numpy(), y_ref.numpy()
         out[name + ".args"] = np.array([up, down, groups, int(flipw)] + (pad if isinstance(pad, list) else [pad] * 4))
         print("conv2d_resample %-24s -> %s pinned" % (name, tuple(y_ref.shape)))
+    # filters other than the 4x4 binomial: none at all with up/down > 1 (negative padding adjustments), non-square 2-D,
+    # non-square kernel, flip_filter.  The filter travels with the vector ("<name>.f", empty = None).
+    fns = torch.rand(3, 5, generator=g)
+    extra = [  # name, cin, cout, kh, kw, up, down, pad, groups, flipw, f, flipf
+        ("x_fnone_up3", 4, 6, 3, 3, 3, 1, 1, 1, True, None, False), ("x_fnone_down3", 4, 6, 2, 2, 1, 3, 0, 2, False, None, False),
+        ("x_fnone_updown", 4, 6, 3, 3, 2, 3, [0, 1, 2, 0], 1, True, None, False),
+        ("x_nonsquare_f_up2", 4, 6, 3, 3, 2, 1, 1, 1, False, fns, False), ("x_nonsquare_f_down2_flip", 6, 4, 1, 1, 1, 2, 1, 1, True, fns, True),
+        ("x_nonsquare_k", 4, 8, 2, 4, 2, 2, [1, 0, 0, 2], 2, False, f, False),
+    ]
+    for name, cin, cout, kh, kw, up, down, pad, groups, flipw, ff, flipf in extra:
+        x = torch.randn(2, cin, 7, 9, generator=g)
+        w = torch.randn(cout, cin // groups, kh, kw, generator=g)
+        y_ref = ref_c2r.conv2d_resample(x, w, f=ff, up=up, down=down, padding=pad, groups=groups, flip_weight=flipw, flip_filter=flipf)
+        y_or = C.conv2d_resample_ref(x, w, f=ff, up=up, down=down, padding=pad, groups=groups, flip_weight=flipw, flip_filter=flipf)
+        assert y_ref.shape == y_or.shape and float((y_ref - y_or).abs().max()) == 0.0, name
+        out[name + ".x"], out[name + ".w"], out[name + ".y"] = x.numpy(), w.numpy(), y_ref.numpy()
+        out[name + ".f"] = np.zeros((0, 0), np.float32) if ff is None else ff.numpy()
+        out[name + ".args"] = np.array([up, down, groups, int(flipw)] + (pad if isinstance(pad, list) else [pad] * 4) + [int(flipf)])
+        print("conv2d_resample %-24s -> %s pinned" % (name, tuple(y_ref.shape)))
     np.savez_compressed(os.path.join(HERE, "conv2d_resample.npz"), **out)
 
 

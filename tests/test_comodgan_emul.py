@@ -21,6 +21,7 @@ from oracle import comodgan_oracle as C  # noqa: E402
 from oracle import migan_oracle as O  # noqa: E402
 from migan_b200 import _abi  # noqa: E402
 sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import build_emul  # noqa: E402
 
 
@@ -209,13 +210,14 @@ def _conv2d_resample(lib, x, w, f, up, down, padding, groups, flip_weight, flip_
 
 
 def test_conv2d_resample_all_branches(emul):
+    from test_oracle import _c2r_cases
     g = np.load(os.path.join(ROOT, "tests", "golden", "conv2d_resample.npz"))
-    f = np.ascontiguousarray(O.setup_filter([1, 3, 3, 1]).numpy())
-    names = sorted({k.rsplit(".", 1)[0] for k in g.files})
-    for name in names:
-        up, down, groups, flipw, p0, p1, p2, p3 = [int(v) for v in g[name + ".args"]]
-        x, w = np.ascontiguousarray(g[name + ".x"]), np.ascontiguousarray(g[name + ".w"])
-        y = _conv2d_resample(emul, x, w, f, up, down, [p0, p1, p2, p3], groups, bool(flipw))
+    cases = list(_c2r_cases(g))
+    assert len(cases) == 15
+    for name, x, w, f, kw in cases:
+        y = _conv2d_resample(emul, np.ascontiguousarray(x.numpy()), np.ascontiguousarray(w.numpy()),
+                             None if f is None else np.ascontiguousarray(f.numpy()), kw["up"], kw["down"], kw["padding"],
+                             kw["groups"], kw["flip_weight"], kw["flip_filter"])
         assert y.shape == g[name + ".y"].shape, name
         assert float(np.abs(y - g[name + ".y"]).max()) < 1e-4, name
 
@@ -357,3 +359,38 @@ def test_staged_tcgen05_route_operands(emul, monkeypatch):
     err = float((y - y_or).abs().max())
     assert err < 1e-3, err
     g.close()
+
+
+def test_conv2d_resample_randomized_sweep(emul):
+    """200 random small configurations -- non-square kernels and filters, f=None with up/down > 1 (negative padding
+    adjustments: Python floor division), up/down in {1,2,3}, asymmetric padding, groups, both flips -- through the
+    emulated kernels against the oracle restatement of conv2d_resample.py:59-154."""
+    rng = np.random.RandomState(0)
+    gen = torch.Generator().manual_seed(0)
+    checked = 0
+    for _ in range(200):
+        groups = int(rng.choice([1, 1, 2, 3]))
+        cin, cout = groups * int(rng.choice([1, 2, 4, 5, 8])), groups * int(rng.choice([1, 2, 3, 4, 16]))
+        kh = int(rng.choice([1, 2, 3, 4]))
+        kw = int(rng.choice([1, 2, 3, 4])) if rng.rand() < 0.3 else kh
+        up, down = int(rng.choice([1, 1, 2, 3])), int(rng.choice([1, 1, 2, 3]))
+        f = [None, O.setup_filter([1, 3, 3, 1]), torch.tensor([1., 2., 1.]) / 4, torch.rand(3, 5, generator=gen)][rng.randint(0, 4)]
+        pad = [int(v) for v in rng.randint(0, 3, size=4)] if rng.rand() < 0.5 else int(rng.randint(0, 3))
+        flipw, flipf = bool(rng.randint(0, 2)), bool(rng.randint(0, 2))
+        h, w, n = int(rng.randint(4, 9)), int(rng.randint(4, 9)), int(rng.randint(1, 3))
+        x = torch.randn(n, cin, h, w, generator=gen)
+        wt = torch.randn(cout, cin // groups, kh, kw, generator=gen)
+        try:
+            want = C.conv2d_resample_ref(x, wt, f=f, up=up, down=down, padding=pad, groups=groups, flip_weight=flipw, flip_filter=flipf)
+        except RuntimeError:
+            continue                      # shapes torch itself rejects (kernel larger than the padded input)
+        if want.numel() == 0:
+            continue
+        f2 = None if f is None else np.ascontiguousarray((torch.outer(f, f) if f.ndim == 1 else f).numpy())
+        got = _conv2d_resample(emul, x.numpy(), wt.numpy(), f2, up, down, pad if isinstance(pad, list) else [pad] * 4, groups,
+                               flipw, flipf)
+        cfg = (cin, cout, kh, kw, up, down, pad, groups, flipw, flipf, None if f is None else tuple(f.shape), h, w)
+        assert got.shape == tuple(want.shape), cfg
+        assert float(np.abs(got - want.numpy()).max()) <= 1e-5 * max(1.0, float(want.abs().max())), cfg
+        checked += 1
+    assert checked > 150

@@ -4,9 +4,13 @@ oracle (oracle/comodgan_oracle.py, pinned bit-exact to the reference) and the fi
 arithmetic is exact fp32 FMA, so the observed error is the summation-order noise floor (~1e-5)."""
 import os
 
+import sys
+
 import numpy as np
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from migan_b200 import comodgan, ops
 from oracle import comodgan_oracle as C
@@ -123,15 +127,12 @@ def test_demo_batch_256(cuda_device):
 
 
 def test_conv2d_resample_reference_vectors(cuda_device):
+    from test_oracle import _c2r_cases
     gold = np.load(os.path.join(GOLDEN, "conv2d_resample.npz"))
-    f = O.setup_filter([1, 3, 3, 1]).to(cuda_device)
-    names = sorted({k.rsplit(".", 1)[0] for k in gold.files})
-    assert len(names) == 9
-    for name in names:
-        up, down, groups, flipw, p0, p1, p2, p3 = [int(v) for v in gold[name + ".args"]]
-        x = torch.from_numpy(gold[name + ".x"]).to(cuda_device)
-        w = torch.from_numpy(gold[name + ".w"]).to(cuda_device)
-        y = ops.conv2d_resample(x, w, f, up=up, down=down, padding=[p0, p1, p2, p3], groups=groups, flip_weight=bool(flipw))
+    cases = list(_c2r_cases(gold))
+    assert len(cases) == 15
+    for name, x, w, f, kw in cases:
+        y = ops.conv2d_resample(x.to(cuda_device), w.to(cuda_device), None if f is None else f.to(cuda_device), **kw)
         assert tuple(y.shape) == gold[name + ".y"].shape, name
         assert float((y.cpu() - torch.from_numpy(gold[name + ".y"])).abs().max()) < 1e-4, name
 

@@ -127,15 +127,24 @@ def test_comodgan_state_dict_spec_counts():
     assert C.num_ws(256) == 14 and C.num_ws(512) == 16               # comodgan.py:371-374
 
 
+def _c2r_cases(g):
+    """(name, x, w, f or None, kwargs) of every vector in tests/golden/conv2d_resample.npz."""
+    from oracle import migan_oracle as O
+    f44 = O.setup_filter([1, 3, 3, 1])
+    for name in sorted({k.rsplit(".", 1)[0] for k in g.files}):
+        a = [int(v) for v in g[name + ".args"]]
+        f = f44
+        if name + ".f" in g.files:
+            f = None if g[name + ".f"].size == 0 else torch.from_numpy(g[name + ".f"])
+        yield name, torch.from_numpy(g[name + ".x"]), torch.from_numpy(g[name + ".w"]), f, dict(
+            up=a[0], down=a[1], groups=a[2], flip_weight=bool(a[3]), padding=a[4:8], flip_filter=bool(a[8]) if len(a) > 8 else False)
+
+
 def test_conv2d_resample_oracle_reproduces_reference_vectors():
     from oracle import comodgan_oracle as C
-    from oracle import migan_oracle as O
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "conv2d_resample.npz"))
-    f = O.setup_filter([1, 3, 3, 1])
-    names = sorted({k.rsplit(".", 1)[0] for k in g.files})
-    assert len(names) == 9
-    for name in names:
-        up, down, groups, flipw, p0, p1, p2, p3 = [int(v) for v in g[name + ".args"]]
-        y = C.conv2d_resample_ref(torch.from_numpy(g[name + ".x"]), torch.from_numpy(g[name + ".w"]), f=f, up=up,
-                                  down=down, padding=[p0, p1, p2, p3], groups=groups, flip_weight=bool(flipw))
+    cases = list(_c2r_cases(g))
+    assert len(cases) == 15
+    for name, x, w, f, kw in cases:
+        y = C.conv2d_resample_ref(x, w, f=f, **kw)
         assert float((y - torch.from_numpy(g[name + ".y"])).abs().max()) <= 1e-4, name
