@@ -397,34 +397,34 @@ int pack_conv(comodgan_ctx* c, ConvL& L, const std::string& p, int cin, int cout
     // raw weight + scale to the device, packed there (same functors the op-level entry point uses)
     float *w_dev = nullptr, *os_dev = nullptr;
     void* tmp[2] = {nullptr, nullptr};
+    const bool flip_weight = (up == 1);                              // stylegan.py:232,291 ("slightly faster")
+    L.KP = up == 1 ? round_up(taps * cin, 16) : round_up(cin, 16);
+    L.NP = up == 1 ? round_up(cout, 64) : round_up(taps * cout, 64);
+    void* bt = nullptr;
     int e = dev_alloc(&tmp[0], w.size() * sizeof(float));
     if (!e) e = dev_alloc(&tmp[1], oscale.size() * sizeof(float));
-    if (e) return fail(ERR_CUDA, "device allocation failed: %s", dev_err(e));
-    w_dev = (float*)tmp[0]; os_dev = (float*)tmp[1];
-    dev_copy(w_dev, w.data(), w.size() * sizeof(float), nullptr);
-    dev_copy(os_dev, oscale.data(), oscale.size() * sizeof(float), nullptr);
-    const bool flip_weight = (up == 1);                              // stylegan.py:232,291 ("slightly faster")
-    void* bt = nullptr;
-    if (up == 1) {
-        L.KP = round_up(taps * cin, 16);
-        L.NP = round_up(cout, 64);
-        e = dev_alloc(&bt, (size_t)L.KP * L.NP * sizeof(float));
-        if (e) return fail(ERR_CUDA, "device allocation failed: %s", dev_err(e));
-        PackWeightK pk{w_dev, os_dev, (float*)bt, cin, k, k, 0, cout, L.KP, L.NP, flip_weight ? 0 : 1, gain};
-        e = (int)ck_launch(pk, (int64_t)L.KP * L.NP, nullptr);
-    } else {
-        L.KP = round_up(cin, 16);
-        L.NP = round_up(taps * cout, 64);
-        e = dev_alloc(&bt, (size_t)L.KP * L.NP * sizeof(float));
-        if (e) return fail(ERR_CUDA, "device allocation failed: %s", dev_err(e));
-        // conv2d_resample.py:140: the transposed conv gets flip_weight = not flip_weight
-        PackWeightTK pk{w_dev, os_dev, (float*)bt, cin, k, k, 0, cout, L.KP, L.NP, flip_weight ? 1 : 0, gain};
-        e = (int)ck_launch(pk, (int64_t)L.KP * L.NP, nullptr);
+    if (!e) e = dev_alloc(&bt, (size_t)L.KP * L.NP * sizeof(float));
+    if (!e) {
+        w_dev = (float*)tmp[0]; os_dev = (float*)tmp[1];
+        e = dev_copy(w_dev, w.data(), w.size() * sizeof(float), nullptr);
+        if (!e) e = dev_copy(os_dev, oscale.data(), oscale.size() * sizeof(float), nullptr);
+    }
+    if (!e) {
+        if (up == 1) {
+            PackWeightK pk{w_dev, os_dev, (float*)bt, cin, k, k, 0, cout, L.KP, L.NP, flip_weight ? 0 : 1, gain};
+            e = (int)ck_launch(pk, (int64_t)L.KP * L.NP, nullptr);
+        } else {   // conv2d_resample.py:140: the transposed conv gets flip_weight = not flip_weight
+            PackWeightTK pk{w_dev, os_dev, (float*)bt, cin, k, k, 0, cout, L.KP, L.NP, flip_weight ? 1 : 0, gain};
+            e = (int)ck_launch(pk, (int64_t)L.KP * L.NP, nullptr);
+        }
     }
     if (!e) e = dev_sync();
-    dev_free(tmp[0]);
-    dev_free(tmp[1]);
-    if (e) return fail(ERR_CUDA, "weight packing failed: %s", dev_err(e));
+    if (tmp[0]) dev_free(tmp[0]);
+    if (tmp[1]) dev_free(tmp[1]);
+    if (e) {
+        if (bt) dev_free(bt);
+        return fail(ERR_CUDA, "weight packing failed: %s", dev_err(e));
+    }
     c->allocs.push_back(bt);
     L.Bt = (float*)bt;
     if (c->use_tc && up == 1 && cin % 4 == 0) {
