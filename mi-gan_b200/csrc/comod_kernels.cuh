@@ -163,9 +163,11 @@ struct Im2colSplit4K { // items = P*KP/4; needs Cg, c0, Ct multiples of 4
 };
 
 // ---- transposed convolution, second half: gather the per-input-pixel products G[p_in][(ky*kw+kx)*Cout + co] -------
-// (G = X * Bt, one GEMM with no wasted MACs) into out[n][y][x][co], y = iy*stride + ky - pt  (F.conv_transpose2d).
+// (G = X * Bt, one GEMM with no wasted MACs -- or one GEMM per tap, see tap_stride) into out[n][y][x][co],
+// y = iy*stride + ky - pt  (F.conv_transpose2d).
 struct Col2imTK {      // items = n*OH*OW*Cout
     const float* g; float* out;
+    int64_t tap_stride;   // elements between the products of consecutive taps: Cout (one GEMM, columns (tap, co)) or rows*NP (one GEMM per tap)
     int H, W, Cout, NP, kh, kw, stride, pt_y, pt_x, OH, OW, Ct, c0;   // out has Ct channels, this group writes [c0, c0+Cout)
     CK_HD void operator()(int64_t i) const {
         const int co = (int)(i % Cout); int64_t t = i / Cout;
@@ -182,7 +184,7 @@ struct Col2imTK {      // items = n*OH*OW*Cout
                 if (X < 0 || X % stride) continue;
                 const int ix = X / stride;
                 if (ix >= W) continue;
-                acc += g[((n * H + iy) * (int64_t)W + ix) * NP + (ky * kw + kx) * Cout + co];
+                acc += g[((n * H + iy) * (int64_t)W + ix) * NP + (ky * kw + kx) * tap_stride + co];
             }
         }
         out[((n * OH + y) * (int64_t)OW + x) * Ct + c0 + co] = acc;

@@ -427,6 +427,42 @@ int pack_conv(comodgan_ctx* c, ConvL& L, const std::string& p, int cin, int cout
     }
     c->allocs.push_back(bt);
     L.Bt = (float*)bt;
+    if (c->use_tc && up > 1 && cin % 64 == 0) {
+        // transposed convolution: one K-major operand per tap, B_t[co][ci] = w[co][ci][tap'] (conv2d_resample.py:140 flip rule)
+        L.KPc = cin;
+        L.NPc = round_up(cout, 64);
+        const size_t per_tap = (size_t)L.NPc * L.KPc;
+        std::vector<float> b(per_tap * taps, 0.f);
+        float maxabs = 0.f;
+        for (int t = 0; t < taps; ++t) {
+            const int ts = flip_weight ? taps - 1 - t : t;               // PackWeightTK: flip when the original flip_weight is set
+            for (int o = 0; o < cout; ++o)
+                for (int ci = 0; ci < cin; ++ci) {
+                    const float v = w[((size_t)o * cin + ci) * taps + ts] * gain * oscale[o];
+                    b[t * per_tap + (size_t)o * L.KPc + ci] = v;
+                    if (std::isfinite(v)) maxabs = std::max(maxabs, std::fabs(v));
+                }
+        }
+        int k2 = maxabs > 0.f ? (int)std::floor(std::log2(16384.0 / (double)maxabs)) : 0;
+        k2 = std::max(-14, std::min(24, k2));
+        const float wscale = std::ldexp(1.0f, k2);
+        L.tc_inv_scale = 1.0f / (wscale * kTcActScale);
+        std::vector<ck_half> hi(b.size()), lo(b.size());
+        for (size_t i = 0; i < b.size(); ++i) {
+            const float sv = b[i] * wscale;
+            hi[i] = ck_f2h(sv);
+            lo[i] = ck_f2h(sv - ck_h2f(hi[i]));
+        }
+        void* d[2] = {nullptr, nullptr};
+        for (int j = 0; j < 2; ++j) {
+            if (int e2 = dev_alloc(&d[j], b.size() * sizeof(ck_half))) return fail(ERR_CUDA, "device allocation failed: %s", dev_err(e2));
+            c->allocs.push_back(d[j]);
+            dev_copy(d[j], j == 0 ? (const void*)hi.data() : (const void*)lo.data(), b.size() * sizeof(ck_half), nullptr);
+        }
+        if (int e2 = dev_sync()) return fail(ERR_CUDA, "weight upload failed: %s", dev_err(e2));
+        L.Bh = (ck_half*)d[0];
+        L.Bl = (ck_half*)d[1];
+    }
     if (c->use_tc && up == 1 && cin % 4 == 0) {
         // B[o][k], k = (ky*kw + kx)*cin + ci: same values as the fp32 operand, K-major, scaled by a power of two so that the
         // largest weight lands in [8192, 16384) (both halves well inside fp16's normal range), split into hi + lo.
@@ -548,6 +584,7 @@ struct Walk {
         const int Ht = (Hin - 1) * L.up + L.k;                        // conv_transpose2d output (padding 0)
         const bool tc = c->use_tc && L.up == 1 && L.Bh != nullptr;   // tcgen05 route (staged, off by default)
         const bool g_sep_tc = tc && L.NPc != cout;
+        const bool tc_up = c->use_tc && L.up > 1 && L.Bh != nullptr;
         size_t per_img = 0;
         if (tc) {
             if (L.down > 1) per_img += (size_t)Hf * Hf * cin;
@@ -557,6 +594,8 @@ struct Walk {
             if (L.down > 1) per_img += (size_t)Hf * Hf * cin;
             if (!direct_a) per_img += (size_t)HWo * L.KP;
             if (g_sep) per_img += (size_t)HWo * L.NP;
+        } else if (tc_up) {
+            per_img += (size_t)HWi * L.KPc + (size_t)L.k * L.k * HWi * L.NPc + (size_t)Ht * Ht * cout;
         } else {
             if (!direct_a) per_img += (size_t)HWi * L.KP;
             per_img += (size_t)HWi * L.NP + (size_t)Ht * Ht * cout;
@@ -574,6 +613,11 @@ struct Walk {
             if (L.down > 1) F = R.take((size_t)chunk * Hf * Hf * cin);
             if (!direct_a) col = R.take((size_t)chunk * HWo * L.KP);
             if (g_sep) G = R.take((size_t)chunk * HWo * L.NP);
+        } else if (tc_up) {
+            ch = reinterpret_cast<ck_half*>(R.take((size_t)chunk * HWi * L.KPc / 2));
+            cl = reinterpret_cast<ck_half*>(R.take((size_t)chunk * HWi * L.KPc / 2));
+            G = R.take((size_t)chunk * L.k * L.k * HWi * L.NPc);
+            T = R.take((size_t)chunk * Ht * Ht * cout);
         } else {
             if (!direct_a) col = R.take((size_t)chunk * HWi * L.KP);
             G = R.take((size_t)chunk * HWi * L.NP);
@@ -615,14 +659,26 @@ struct Walk {
             } else {
                 // conv2d_resample.py:94-98,124-142 with k=3, up=2, padding=1, 4x4 filter: px0 = 1+2-2 = 1, px1 = 1+1-1 = 1,
                 // pxt = 0: conv_transpose2d(stride 2, padding 0) then upfirdn2d(pad 1,1,1,1, gain 4).
-                const float* A = in_c;
-                if (!direct_a) {
-                    R.im2col(in_c, scale_c, col, cnt, Hin, Hin, cin, 0, cin, 1, 1, 1, 0, 0, Hin, Hin, L.KP);
-                    A = col;
+                if (tc_up) {
+                    // one tcgen05 GEMM per tap: G[tap][p][NPc] = X[p][:] * B_tap[:][:]^T (N = cout is a power-of-two number of
+                    // N tiles, 9*cout is not), gathered by the same col2im with tap_stride = rows * NPc
+                    R.im2col_split(in_c, scale_c, ch, cl, kTcActScale, cnt, Hin, Hin, cin, 1, 1, 1, 0, 0, Hin, Hin, L.KPc);
+                    const int64_t rows = cnt * HWi;
+                    for (int t = 0; t < L.k * L.k; ++t)
+                        R.gemm_tc_(ch, cl, L.Bh + (size_t)t * L.NPc * L.KPc, L.Bl + (size_t)t * L.NPc * L.KPc, L.tc_inv_scale,
+                                   G + t * rows * L.NPc, (int)cnt, Hin, L.KPc, L.NPc);
+                    Col2imTK ct{G, T, rows * L.NPc, Hin, Hin, cout, L.NPc, L.k, L.k, L.up, 0, 0, Ht, Ht, cout, 0};
+                    R.launch(ct, cnt * Ht * Ht * cout);
+                } else {
+                    const float* A = in_c;
+                    if (!direct_a) {
+                        R.im2col(in_c, scale_c, col, cnt, Hin, Hin, cin, 0, cin, 1, 1, 1, 0, 0, Hin, Hin, L.KP);
+                        A = col;
+                    }
+                    R.gemm(A, L.Bt, G, cnt * HWi, L.KP, L.NP);
+                    Col2imTK ct{G, T, (int64_t)cout, Hin, Hin, cout, L.NP, L.k, L.k, L.up, 0, 0, Ht, Ht, cout, 0};
+                    R.launch(ct, cnt * Ht * Ht * cout);
                 }
-                R.gemm(A, L.Bt, G, cnt * HWi, L.KP, L.NP);
-                Col2imTK ct{G, T, Hin, Hin, cout, L.NP, L.k, L.k, L.up, 0, 0, Ht, Ht, cout, 0};
-                R.launch(ct, cnt * Ht * Ht * cout);
                 const int fw = 4;
                 int px0 = L.k / 2 + (fw + L.up - 1) / 2 - (L.k - 1);
                 int px1 = L.k / 2 + (fw - L.up) / 2 - (L.k - L.up);
@@ -963,7 +1019,7 @@ int b200_conv2d_resample(const float* x, const float* w, const float* f, float* 
                 R.launch(PackWeightTK{w, nullptr, bt, cin_g, kh, kw, gi * cout_g, cout_g, KP, NP, flipw ? 0 : 1, 1.f}, (int64_t)KP * NP);
                 R.im2col(cur, nullptr, col, n, H, W, C, gi * cin_g, cin_g, 1, 1, 1, 0, 0, H, W, KP);
                 R.gemm(col, bt, g, (int64_t)n * H * W, KP, NP);
-                Col2imTK ct{g, o, H, W, cout_g, NP, kh, kw, stride, pt_y, pt_x, OH, OW, cout, gi * cout_g};
+                Col2imTK ct{g, o, (int64_t)cout_g, H, W, cout_g, NP, kh, kw, stride, pt_y, pt_x, OH, OW, cout, gi * cout_g};
                 R.launch(ct, (int64_t)n * OH * OW * cout_g);
             }
             R.release(m);
