@@ -357,7 +357,18 @@ def run_b200(args):
             json.dump({"res": R, "batch": B, "path": args.path, "hbm_peak_GBps": peak, "launches": table}, f, indent=1)
 
     cpu = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline:
+        try:   # parity in the same run, image 0 of the timed batch against the CPU reference algorithm
+            from oracle import migan_oracle as O  # checker / CPU baseline only
+            y0 = model(x)[:1].cpu()
+            ref = O.generator_forward(O.make_state_dict(R, seed=1), x_host[:1], R)
+            d = (y0 - ref).abs()
+            parity = {"max_abs": float(d.max()), "mean_abs": float(d.mean()), "ref_abs_max": float(ref.abs().max()),
+                      "isclose_rtol_1e-3_mismatch_frac": float((~torch.isclose(y0, ref, rtol=1e-3)).float().mean()),
+                      "against": "oracle port (bit-exact with the reference on the committed fixtures), image 0 of the timed batch"}
+        except Exception as exc:
+            parity = {"error": str(exc)[:200]}
         rate, iters, cores = cpu_reference_forward_rate(R, seconds=12.0, max_iters=40)
         cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
                "sample": "%d bs=1 forwards of migan-%d with the oracle port (torch %s CPU ops, %d threads)"
@@ -377,7 +388,7 @@ def run_b200(args):
                    "e2e": "K host batches submitted back to back through migan_forward_host_async (pinned H2D + forward + D2H "
                           "per batch, two staging slots so the copies of batch t+1 / t-1 run under the kernels of batch t), timed until the last "
                           "output landed in host memory"},
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8,
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8,
         "gpu_launches": launches_per_step * K,
     }
     print_json(json.dumps(line), flush=True)
