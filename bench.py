@@ -11,6 +11,7 @@ the outputs are all-gathered over NCCL.  Prints ONE JSON line (rank 0).
   e2e          same metric through the host-buffer C-ABI call (pinned H2D + forward + D2H per step)
   roofline     dominant kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json HBM copy rate
   cpu_baseline the reference algorithm (oracle port, torch CPU ops) on this box's host cores
+  parity       max-abs / mean-abs error of image 0 of the timed batch vs the CPU reference algorithm (same run)
   clocks       SM clock / throttle reasons sampled during the timed region
 """
 import argparse
