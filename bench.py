@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--comod-gemm", default=None, choices=["simt", "tc"],
                     help="comodgan workload: GEMM engine (tc = staged tcgen05 route, not yet run on hardware)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true",
+                    help="N > 1: skip the output all-gather (shows what the collective costs; not the north_star configuration)")
     ap.add_argument("--profile-out", default=None, help="write the per-launch table (JSON) here")
     args = ap.parse_args()
     if args.res is None:
@@ -225,7 +227,7 @@ def run_b200(args):
     model = model.to(dev).eval()
     x_host = synthetic.synthetic_input(R, B, seed=1234 + rank).pin_memory()
     x = x_host.to(dev)
-    sharded = parallel.ShardedGenerator(model) if world > 1 else None
+    sharded = parallel.ShardedGenerator(model) if (world > 1 and not args.no_gather) else None
     if sharded is not None:
         sharded.check_replicas(model.state_dict())
 
@@ -380,7 +382,7 @@ def run_b200(args):
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.path != "tc_fast" else "f16",
         "data": "synthetic",
-        "config": {"workload": "migan-%d Generator.forward, %d images/GPU%s" % (R, B, ", NCCL all-gather of outputs" if world > 1 else ""),
+        "config": {"workload": "migan-%d Generator.forward, %d images/GPU%s" % (R, B, ", NCCL all-gather of outputs" if sharded is not None else (", no gather" if world > 1 else "")),
                    "path": args.path, "arithmetic": "fp32 CUDA-core depthwise/FIR; 1x1 convs on tcgen05 as fp16 hi/lo 3-pass split with fp32 accumulate"
                    if args.path == "tc" else args.path,
                    "global_batch": world * B, "weights": "seeded export-style random (unit-L2 filters)",
