@@ -231,6 +231,9 @@ int migan_create(int resolution, int device, migan_ctx** out) {
     while ((1 << (log2res + 1)) <= resolution) ++log2res;
     if (resolution < 8 || (1 << log2res) != resolution || resolution > 4096)
         return fail(MIGAN_ERR_INVALID, "resolution must be a power of two in [8, 4096], got %d", resolution);
+    if (device >= 0 && channels(resolution) < 64)
+        return fail(MIGAN_ERR_INVALID, "resolution %d has %d-channel levels; the kernels are built for >= 64 channels per level "
+                    "(resolutions up to 512, i.e. every released MI-GAN model)", resolution, channels(resolution));
     std::unique_ptr<migan_ctx> c(new migan_ctx);
     c->resolution = resolution;
     c->device = device;

@@ -207,3 +207,12 @@ def test_reference_export_script_accepts_b200_generator(lib, monkeypatch):
         y_src = src(x, noise_mode="const")
     y_or = O.generator_forward({k: v.detach() for k, v in b.items()}, x, R)
     assert float((y_src - y_or).abs().max()) < 1e-4            # SURVEY 8c pin (1): 1.05e-5 at output scale 13.6
+
+
+def test_resolutions_above_512_are_rejected_up_front(lib):
+    """min(32768 // R, 512) drops below 64 channels for R > 512: not built (no released model); fail at create, not mid-forward.
+    A description-only context (device -1: names and shapes) is still available."""
+    h = ctypes.c_void_p()
+    assert lib.migan_create(1024, 0, ctypes.byref(h)) == 1 and b"64 channels" in lib.migan_last_error()
+    assert lib.migan_create(1024, -1, ctypes.byref(h)) == 0
+    lib.migan_destroy(h)
