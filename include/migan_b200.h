@@ -118,9 +118,9 @@ int migan_set_tap(migan_ctx* ctx, const char* name, float* dst);
  * past the end).  shape = {C, H, W} of one image. */
 int migan_tap_info(const migan_ctx* ctx, int path, int index, const char** name, int shape[3]);
 
-/* Debug: clock64 stamps of CTA 0 of the tcgen05 kernel, [role 4][tile 64][event 16] u64, recorded for
- * the layer shape named by the environment variable MIGAN_TC_TRACE="res,cin,cout" (tools/tc_trace.py). */
-int migan_debug_read_tc_trace(unsigned long long* host_4096);
+/* Debug: every pipeline wait inside the tcgen05 kernel is bounded (seconds of wall-clock time); a wait that gives up records
+ * (wait code | parity << 12 | block << 16) in a host-mapped word and traps.  Returns that record for `device` (0: none). */
+int migan_debug_tc_timeout(int device);
 
 /* upfirdn2d(x[n,c,h,w], f[fh,fw]) -> y[n,c,oh,ow], oh = (h*upy + pady0 + pady1 - fh + downy) / downy
  * (upfirdn2d.cpp:32-33).  f == NULL means the 1x1 identity filter.  Device pointers. */

@@ -78,6 +78,10 @@ struct SepConv {
     float tc_inv_scale = 1.f; // 1 / (kActSplitScale * 2^k)
     float* fir16 = nullptr;   // [16][cin] (down) or [16][cout] (up), tap-major
     float* noise_dev = nullptr;  // [res_out^2] = noise_const * noise_strength
+    // fused up-sampling prologue of the NEXT layer (sepconv_tc SEPCONV_SRC_UP): needs channel-uniform FIR taps
+    bool up_uniform = false;
+    float up_taps_s2[16] = {0};      // taps * sqrt(2)
+    float* noise_s2_dev = nullptr;   // noise * sqrt(2)
 };
 
 struct ToRgb {
@@ -99,6 +103,8 @@ struct Step {
     const ToRgb* T = nullptr;
     const float* in = nullptr;
     const float* aux = nullptr;  // skip tensor / low-res image / noise
+    const float* aux2 = nullptr; // fused up-sampling prologue: the low-resolution raw tensor
+    bool fused_stem = false, fused_up = false;
     float* out = nullptr;
     __half* hi = nullptr;
     __half* lo = nullptr;
@@ -143,6 +149,8 @@ struct migan_ctx {
     // encoder
     float* fromrgb_w = nullptr;  // [C0][4]
     float* fromrgb_b = nullptr;
+    float* fromrgb_w_s2 = nullptr;  // * sqrt(2): stem recomputed in the prologue of encoder.b{R}.conv1
+    float* fromrgb_b_s2 = nullptr;
     std::vector<SepConv> enc1, enc2;  // per enc_res entry
     // synthesis
     std::vector<SepConv> syn1, syn2;  // per syn_res entry
@@ -160,6 +168,7 @@ struct migan_ctx {
     std::vector<cudaEvent_t> host_events;
     cudaEvent_t slot_compute_done[2] = {nullptr, nullptr}, slot_out_done[2] = {nullptr, nullptr};
     bool slot_used[2] = {false, false};
+    const void* slot_base[2] = {nullptr, nullptr};   // staging memory each slot last used (re-ordered after the caller's stream when it changes)
     unsigned host_calls = 0;
     int tap_cache_path = -1;          // tap enumeration cache (migan_tap_info)
     std::vector<std::pair<std::string, std::array<int, 3>>> tap_cache;
@@ -414,6 +423,13 @@ static int pack_sepconv(migan_ctx* ctx, SepConv& L, ArenaBuilder& ab, std::vecto
         for (int c = 0; c < cf; ++c)
             for (int t = 0; t < 16; ++t) d[t * cf + c] = f[c * 16 + t];
         fix.push_back({reinterpret_cast<void**>(&L.fir16), off});
+        if (L.up) {   // the fused prologue keeps the 16 taps in registers: they must not depend on the channel
+            L.up_uniform = true;
+            for (int c = 1; c < cf && L.up_uniform; ++c)
+                for (int t = 0; t < 16; ++t)
+                    if (f[c * 16 + t] != f[t]) { L.up_uniform = false; break; }
+            for (int t = 0; t < 16; ++t) L.up_taps_s2[t] = f[t] * 1.41421356237309515f;
+        }
     }
     if (L.up) {
         // The kernels implement zero insertion; check filter_const is that pattern (migan_inference.py:83-85).
@@ -433,6 +449,12 @@ static int pack_sepconv(migan_ctx* ctx, SepConv& L, ArenaBuilder& ab, std::vecto
         float* d = reinterpret_cast<float*>(ab.bytes.data() + off);
         for (size_t i = 0; i < nc.size(); ++i) d[i] = nc[i] * ns;  // migan_inference.py:166
         fix.push_back({reinterpret_cast<void**>(&L.noise_dev), off});
+        if (L.up) {
+            size_t off2 = ab.alloc(sizeof(float) * nc.size());
+            float* d2 = reinterpret_cast<float*>(ab.bytes.data() + off2);
+            for (size_t i = 0; i < nc.size(); ++i) d2[i] = nc[i] * ns * 1.41421356237309515f;
+            fix.push_back({reinterpret_cast<void**>(&L.noise_s2_dev), off2});
+        }
     }
     return MIGAN_OK;
 }
@@ -454,6 +476,13 @@ int migan_finalize_weights(migan_ctx* ctx) {
         memcpy(ab.bytes.data() + ob, b.data(), sizeof(float) * b.size());
         fix.push_back({reinterpret_cast<void**>(&ctx->fromrgb_w), ow});
         fix.push_back({reinterpret_cast<void**>(&ctx->fromrgb_b), ob});
+        size_t ow2 = ab.alloc(sizeof(float) * w.size()), ob2 = ab.alloc(sizeof(float) * b.size());
+        float* dw2 = reinterpret_cast<float*>(ab.bytes.data() + ow2);
+        float* db2 = reinterpret_cast<float*>(ab.bytes.data() + ob2);
+        for (size_t i = 0; i < w.size(); ++i) dw2[i] = w[i] * 1.41421356237309515f;
+        for (size_t i = 0; i < b.size(); ++i) db2[i] = b[i] * 1.41421356237309515f;
+        fix.push_back({reinterpret_cast<void**>(&ctx->fromrgb_w_s2), ow2});
+        fix.push_back({reinterpret_cast<void**>(&ctx->fromrgb_b_s2), ob2});
     }
     for (auto* vec : {&ctx->enc1, &ctx->enc2, &ctx->syn1, &ctx->syn2})
         for (SepConv& L : *vec) {
@@ -527,6 +556,14 @@ size_t migan_host_staging_bytes(const migan_ctx* ctx, int n) {
 
 namespace {
 
+// What the tensor-core kernel's prologue rebuilds on chip instead of reading it from HBM (sepconv_tc.h SepconvSource).
+struct Fuse {
+    bool stem = false;              // input = fromrgb(x): the stem tensor never exists (encoder.b{R}.conv1)
+    const SepConv* up = nullptr;    // input = lrelu_agc(up2(up_t) + noise) + skip, `up` = the preceding up-sampling layer
+    const float* up_t = nullptr;    // its raw low-resolution 1x1 output
+    bool defer_up = false;          // this layer IS the up-sampling layer: emit only the raw 1x1 conv
+};
+
 struct PlanBuilder {
     migan_ctx* c;
     int n, path;
@@ -545,11 +582,17 @@ struct PlanBuilder {
         s.tap = name; s.tap_src = src; s.tapC = C; s.tapH = H; s.tapW = W; s.tap_planar = planar; s.tap_flags = flags;
     }
 
+    static int fuse_mask() {            // MIGAN_FUSE bit 0: UP, bit 1: STEM (debug / A-B measurements; default all on)
+        const char* e = getenv("MIGAN_FUSE");
+        return e ? atoi(e) : 3;
+    }
+
     // Emit one SeparableConv2d reading `in` (NHWC [n,res_in,res_in,cin]); `skip` is added after the
     // final activation (decoder conv1, migan_inference.py:304-305).  Returns the output pointer.
     // in_idx: scratch index holding `in` (or -1 if it is a feat buffer); out_fixed: write there if non-null.
     int emit_sepconv(const SepConv& L, const float* in, int in_idx, float* out_fixed, const float* skip, int& out_idx, float*& out_ptr,
-                     const migan::SepconvTcRgb* rgb = nullptr, const std::string& rgb_tap = std::string(), int rgb_flags = 0) {
+                     const migan::SepconvTcRgb* rgb = nullptr, const std::string& rgb_tap = std::string(), int rgb_flags = 0,
+                     const Fuse& fuse = Fuse()) {
         const int t1 = other(in_idx), t2 = other(in_idx, t1);
         const bool tc = (path != MIGAN_PATH_SIMT);
         const float* gemm_in = nullptr;
@@ -572,7 +615,7 @@ struct PlanBuilder {
             steps.push_back(s);
             gemm_in = S[t1];
         } else if (L.cout >= 512 && !rgb) {
-            // Cout spans 4 CTA N tiles: a fused prologue would re-run the depthwise stage 4x, so run it once as its
+            // Cout spans 4 accumulator regions: a fused prologue would re-run the depthwise stage, so run it once as its
             // own kernel and hand the GEMM a pre-split operand (these layers are small: res <= 64)
             Step s; s.kind = K_DW; s.L = &L; s.in = in; s.n = n; s.H = L.res_in; s.W = L.res_in; s.C = L.cin;
             s.hi = reinterpret_cast<__half*>(S[t1]);
@@ -584,7 +627,7 @@ struct PlanBuilder {
         // 1x1 conv at res_pw
         float* pw_out;
         int pw_idx;
-        const bool raw = L.up;  // up layers: noise/act happen after the FIR (K_UP2)
+        const bool raw = L.up;  // up layers: noise/act happen after the FIR (K_UP2, or the next layer's fused prologue)
         if (raw) { pw_out = S[t2]; pw_idx = t2; }
         else if (out_fixed) { pw_out = out_fixed; pw_idx = -1; }
         else { pw_out = S[t2]; pw_idx = t2; }
@@ -596,8 +639,24 @@ struct PlanBuilder {
                 s.kind = K_SEPCONV_TC;
                 s.in = presplit ? nullptr : in;  // pre-split A operand from K_DWDOWN / K_DW
                 s.hi = ghi; s.lo = glo;
-                const char* err = migan::sepconv_tc_plan(&s.tc, path == MIGAN_PATH_TC_FAST ? 1 : 3, s.in, ghi, glo, L.w9_tc, L.bias_tc,
-                                                         L.pw_hi, L.pw_lo, L.tc_inv_scale, s.aux, pw_out, n, L.res_pw, L.cin, L.cout, s.act, rgb);
+                migan::SepconvTcDesc d;
+                d.passes = (path == MIGAN_PATH_TC_FAST) ? 1 : 3;
+                d.source = presplit ? migan::SEPCONV_SRC_SPLIT : migan::SEPCONV_SRC_NHWC;
+                d.in_f32 = s.in; d.a_hi = ghi; d.a_lo = glo;
+                d.w9 = L.w9_tc; d.bias = L.bias_tc; d.w_hi = L.pw_hi; d.w_lo = L.pw_lo; d.inv_scale = L.tc_inv_scale;
+                d.noise = s.aux; d.out = pw_out; d.n = n; d.res = L.res_pw; d.cin = L.cin; d.cout = L.cout; d.act = s.act; d.rgb = rgb;
+                if (fuse.stem) {
+                    d.source = migan::SEPCONV_SRC_STEM; d.in_f32 = nullptr;
+                    d.stem_w = c->fromrgb_w_s2; d.stem_b = c->fromrgb_b_s2;
+                    s.in = nullptr; s.io_flags |= PTR_X; s.fused_stem = true;
+                } else if (fuse.up) {
+                    d.source = migan::SEPCONV_SRC_UP;      // d.in_f32 = `in` = the encoder feature (skip tensor)
+                    d.up_t = fuse.up_t;
+                    d.up_noise = fuse.up->noise ? fuse.up->noise_s2_dev : nullptr;
+                    memcpy(d.up_taps, fuse.up->up_taps_s2, sizeof(d.up_taps));
+                    s.aux2 = fuse.up_t; s.fused_up = true;
+                }
+                const char* err = migan::sepconv_tc_plan_ex(&s.tc, d);
                 if (rgb) {
                     s.io_flags |= rgb_flags;
                     s.tap2 = rgb_tap; s.tap2_src = rgb->img_out; s.tap2C = 3; s.tap2H = L.res_pw; s.tap2W = L.res_pw; s.tap2_flags = rgb_flags;
@@ -610,6 +669,7 @@ struct PlanBuilder {
             steps.push_back(s);
         }
         out_ptr = pw_out; out_idx = pw_idx;
+        if (L.up && fuse.defer_up) return MIGAN_OK;   // FIR + noise + activation + skip happen in the next layer's prologue
         if (L.up) {
             float* up_out; int up_idx;
             if (out_fixed) { up_out = out_fixed; up_idx = -1; }
@@ -633,8 +693,13 @@ struct PlanBuilder {
         for (int i = 0; i < 3; ++i) { S[i] = reinterpret_cast<float*>(base + off); off += scratch_bytes(c, n); }
         for (int i = 0; i < 2; ++i) { IMG[i] = reinterpret_cast<float*>(base + off); off += img_bytes(c, n); }
         const int R = c->resolution;
+        const bool tcp = (path != MIGAN_PATH_SIMT);
+        const int fm = fuse_mask();
         // ---- encoder (migan_inference.py:235-246) ----
-        {
+        // The stem (fromrgb + activation, :193-196) is recomputed inside encoder.b{R}.conv1's prologue when that layer runs
+        // on the fused tensor-core kernel with 8 x 16 tiles; otherwise it is its own kernel.
+        const bool fuse_stem = tcp && (fm & 2) && R >= 16 && channels(R) < 512;
+        if (!fuse_stem) {
             Step s; s.kind = K_STEM; s.io_flags = PTR_X; s.out = S[0]; s.n = n; s.H = R; s.W = R; s.C = channels(R);
             set_tap(s, "encoder.b" + std::to_string(R) + ".fromrgb", S[0], channels(R), R, R);
             steps.push_back(s);
@@ -644,7 +709,9 @@ struct PlanBuilder {
         for (size_t i = 0; i < c->enc_res.size(); ++i) {
             const int r = c->enc_res[i];
             int oi; float* op;
-            int rc = emit_sepconv(c->enc1[i], cur, cur_idx, feat[r], nullptr, oi, op);  // feat = conv1(x)
+            Fuse f1;
+            f1.stem = (i == 0 && fuse_stem);
+            int rc = emit_sepconv(c->enc1[i], cur, cur_idx, feat[r], nullptr, oi, op, nullptr, std::string(), 0, f1);  // feat = conv1(x)
             if (rc) return rc;
             rc = emit_sepconv(c->enc2[i], feat[r], -1, nullptr, nullptr, oi, op);      // x = conv2(feat)
             if (rc) return rc;
@@ -655,23 +722,31 @@ struct PlanBuilder {
         for (size_t i = 0; i < c->syn_res.size(); ++i) {
             const int r = c->syn_res[i];
             int oi; float* op;
-            int rc = emit_sepconv(c->syn1[i], cur, cur_idx, nullptr, feat[r], oi, op);  // x = conv1(x) + enc_feat
-            if (rc) return rc;
-            cur = op; cur_idx = oi;
             const bool last = (i + 1 == c->syn_res.size());
             const int img_next = (img_cur < 0) ? 0 : 1 - img_cur;
             const float* img_lo = (img_cur >= 0) ? IMG[img_cur] : nullptr;
             float* img_out = last ? nullptr : IMG[img_next];      // last level: the caller's y (bound at launch)
             const ToRgb& T = c->torgb[i];
-            const bool fuse = (path != MIGAN_PATH_SIMT) && channels(r) <= 128;
-            if (fuse) {
+            const bool fuse_rgb = tcp && channels(r) <= 128;
+            // conv1's FIR + noise + activation + skip can be rebuilt in conv2's prologue (the up-sampled tensor then never
+            // exists in HBM) when conv2 runs its depthwise stage in the tensor-core kernel with 8 x 16 tiles.
+            const SepConv& L1 = c->syn1[i];
+            const bool fuse_up = tcp && (fm & 1) && L1.up && L1.up_uniform && r >= 16 && (channels(r) < 512 || fuse_rgb);
+            Fuse f1; f1.defer_up = fuse_up;
+            int rc = emit_sepconv(L1, cur, cur_idx, nullptr, feat[r], oi, op, nullptr, std::string(), 0, f1);  // x = conv1(x) + enc_feat
+            if (rc) return rc;
+            cur = op; cur_idx = oi;
+            Fuse f2;
+            const float* in2 = cur;
+            if (fuse_up) { f2.up = &L1; f2.up_t = cur; in2 = feat[r]; }   // scratch bookkeeping still protects `cur` (= t)
+            if (fuse_rgb) {
                 migan::SepconvTcRgb rgb;
                 rgb.w = T.w; rgb.b = T.b; rgb.fir = T.fir; rgb.img_lo = img_lo; rgb.img_out = img_out; rgb.store_out = last ? 0 : 1;
-                rc = emit_sepconv(c->syn2[i], cur, cur_idx, nullptr, nullptr, oi, op, &rgb, T.p + "img", last ? PTR_Y : 0);
+                rc = emit_sepconv(c->syn2[i], in2, cur_idx, nullptr, nullptr, oi, op, &rgb, T.p + "img", last ? PTR_Y : 0, f2);
                 if (rc) return rc;
                 cur = op; cur_idx = oi;
             } else {
-                rc = emit_sepconv(c->syn2[i], cur, cur_idx, nullptr, nullptr, oi, op);
+                rc = emit_sepconv(c->syn2[i], in2, cur_idx, nullptr, nullptr, oi, op, nullptr, std::string(), 0, f2);
                 if (rc) return rc;
                 cur = op; cur_idx = oi;
                 Step s; s.kind = K_TORGB; s.T = &T; s.in = cur; s.n = n; s.H = r; s.W = r; s.C = channels(r);
@@ -711,7 +786,9 @@ struct PlanBuilder {
                 case K_GEMM_SIMT: s.alg_bytes = px * (s.L->cin + s.L->cout) * f; s.flops = px * 2.0 * s.L->cin * s.L->cout; break;
                 case K_SEPCONV_TC:
                     s.alg_bytes = px * (s.L->cin + s.L->cout) * f;
-                    s.flops = px * (2.0 * s.L->cin * s.L->cout + (s.in ? 18.0 * s.L->cin : 0.0));
+                    s.flops = px * (2.0 * s.L->cin * s.L->cout + ((s.in || s.fused_stem) ? 18.0 * s.L->cin : 0.0));
+                    if (s.fused_stem) { s.alg_bytes = px * (4 + s.L->cout) * f; s.flops += px * s.L->cin * 8.0; }
+                    if (s.fused_up) { s.alg_bytes += px * 0.25 * s.L->cin * f; s.flops += px * s.L->cin * 8.0; }   // + the low-res tensor
                     if (!s.tap2.empty()) {   // fused torgb: + image in/out, - feature map if it is not stored
                         s.alg_bytes += px * 3.75 * f;
                         s.flops += px * s.L->cout * 6;
@@ -737,7 +814,7 @@ int build_plan(migan_ctx* ctx, int n, int path, void* ws) {
     return MIGAN_OK;
 }
 
-int run_step(migan_ctx* ctx, const Step& s, const float* x, float* y, cudaStream_t st) {
+int run_step(migan_ctx* ctx, Step& s, const float* x, float* y, cudaStream_t st) {
     const float* in = (s.io_flags & PTR_X) ? x : s.in;
     float* out = (s.io_flags & PTR_Y) ? y : s.out;
     cudaError_t e = cudaSuccess;
@@ -756,7 +833,7 @@ int run_step(migan_ctx* ctx, const Step& s, const float* x, float* y, cudaStream
                                            s.aux, s.H * s.W, s.act, st);
             break;
         case K_SEPCONV_TC:
-            e = migan::launch_sepconv_tc(s.tc, st, (s.io_flags & PTR_Y) ? y : nullptr);
+            e = migan::launch_sepconv_tc(s.tc, st, (s.io_flags & PTR_Y) ? y : nullptr, s.fused_stem ? x : nullptr);
             break;
         case K_UP2:
             e = migan::launch_up2(in, s.L->fir16, s.L->noise ? s.L->noise_dev : nullptr, s.aux, out, s.n, s.H, s.W, s.C, st);
@@ -817,7 +894,7 @@ int migan_forward(migan_ctx* ctx, const float* x, float* y, int n, void* workspa
         }
     }
     size_t i = 0;
-    for (const Step& s : ctx->plan.steps) {
+    for (Step& s : ctx->plan.steps) {
         if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->events[2 * i], st));
         int rc = run_step(ctx, s, x, y, st);
         if (rc) return rc;
@@ -898,12 +975,19 @@ static int forward_host_enqueue(migan_ctx* ctx, const float* x_host, float* y_ho
     cudaEvent_t ev_start = ev[2 * M];
     const int m = n / M;
     const size_t xs = (size_t)m * 4 * ctx->resolution * ctx->resolution, ys = (size_t)m * 3 * ctx->resolution * ctx->resolution;
-    // The copy-in stream does NOT wait for the caller's stream: x_host is host memory (valid from the call on) and the
-    // only device hazard -- the staging slot still being read by the forward that used it two calls ago -- is covered by
-    // slot_compute_done below.  Waiting on `stream` here would serialise the H2D of batch t+1 behind the kernels of
-    // batch t, which is exactly the overlap the two slots exist for.  The copy-out stream only ever waits for the
-    // compute-done events recorded after this point.
-    (void)ev_start;
+    // In steady state the copy-in stream does NOT wait for the caller's stream: x_host is host memory (valid from the call
+    // on) and the only device hazard -- the staging slot still being read by the forward that used it two calls ago -- is
+    // covered by slot_compute_done below.  Waiting on `stream` here would serialise the H2D of batch t+1 behind the kernels
+    // of batch t, which is exactly the overlap the two slots exist for.
+    // The FIRST use of a staging area is different: the memory may have just been handed over by a stream-ordered
+    // allocator (torch's caching allocator assumes same-stream reuse), so work still pending on the caller's stream may be
+    // using it.  Order both copy streams after the caller's stream once, whenever a slot sees new memory.
+    if (!ctx->slot_used[slot] || ctx->slot_base[slot] != sbase) {
+        CUDA_TRY(cudaEventRecord(ev_start, st));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ev_start, 0));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ev_start, 0));
+        ctx->slot_base[slot] = sbase;
+    }
     if (ctx->slot_used[slot]) {
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->slot_compute_done[slot], 0));   // xd[slot] free again
         CUDA_TRY(cudaStreamWaitEvent(st, ctx->slot_out_done[slot], 0));              // yd[slot] copied out
@@ -1036,11 +1120,7 @@ int migan_tap_info(const migan_ctx* ctx, int path, int index, const char** name,
     return MIGAN_OK;
 }
 
-int migan_debug_read_tc_trace(unsigned long long* host_4096) {
-    cudaError_t e = migan::sepconv_tc_read_trace(host_4096);
-    if (e != cudaSuccess) return fail(MIGAN_ERR_CUDA, "trace read failed: %s", cudaGetErrorString(e));
-    return MIGAN_OK;
-}
+int migan_debug_tc_timeout(int device) { return migan::sepconv_tc_timeout_record(device); }
 
 int b200_upfirdn2d(const float* x, const float* f, float* y, int n, int c, int h, int w, int fh, int fw,
                    int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1,

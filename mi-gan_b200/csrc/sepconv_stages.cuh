@@ -1,0 +1,278 @@
+// CUDA-core stages of the fused SeparableConv2d kernel (sepconv_tc.cu) that work on shared-memory tiles.
+//
+// Every function here is written against plain pointers into one pipeline stage of shared memory and takes the
+// worker index `tg` (0..127: the thread's index inside its 128-thread prologue group) as an argument, with no
+// barrier, shuffle or special register inside.  That is deliberate: the same source compiles as plain C++
+// (-DMIGAN_EMULATE, tests/emul/build_stages.py) where a test loops tg = 0..127 over a host buffer filled the way
+// the TMA unit fills the stage (box layout, out-of-bounds zero fill), so the halo / polyphase / swizzle index math is
+// checked against the oracle on a machine without a GPU (tests/test_stages_emul.py).  The emulation build is TEST
+// INFRASTRUCTURE; the product library is compiled without the macro.
+//
+// Stage layouts (one 32-channel chunk of one 8 x 16 output tile at origin (y0, x0), TMA boxes, no swizzle):
+//   IN   [10 rows][18 cols][32 ch] fp32   rows y0-1 .. y0+8, cols x0-1 .. x0+16: the depthwise conv's input + halo
+//   T    [ 6 rows][10 cols][32 ch] fp32   UP: raw 1x1 output of the up-sampling layer, rows y0/2-1 .. y0/2+4
+//   NZ   [10 rows][20 cols]        fp32   UP: noise map rows y0-1 .. y0+8, cols x0-2 .. x0+17 (16-byte rows)
+//   XA   [4 planes][10 rows][20 cols] fp32 STEM: the generator input x (NCHW planes), same window as NZ
+//   DIN  [20 rows][36 cols][16 ch] fp32   DOWN: input rows 2*y0-2 .. 2*y0+17, cols 2*x0-2 .. 2*x0+33 (16-ch chunk)
+// A operand (one K block of 64 channels, M = 128 pixel rows): fp16 hi and lo planes, UMMA K-major SWIZZLE_128B:
+//   byte(m, k) = (m >> 3) * 1024 + (m & 7) * 128 + (((k >> 3) ^ (m & 7)) << 4) + (k & 7) * 2
+#pragma once
+#include <stdint.h>
+
+#ifdef MIGAN_EMULATE
+#include <math.h>
+#include <string.h>
+#define SC_DEV static inline
+#else
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#define SC_DEV __device__ __forceinline__
+#endif
+
+namespace migan {
+namespace stages {
+
+constexpr float kAlpha = 0.2f;                 // lrelu_agc (migan_inference.py:20-28): alpha, gain sqrt 2, clamp 256
+constexpr float kGain = 1.41421356237309515f;
+constexpr float kClamp = 256.0f;
+constexpr float kSplit = 64.0f;                // power-of-two scale of the fp16 hi/lo split (common.cuh kActSplitScale)
+
+typedef unsigned long long u64;
+
+#ifdef MIGAN_EMULATE
+struct f2 { float x, y; };
+struct alignas(16) f4 { float x, y, z, w; };
+SC_DEV u64 pk(float lo, float hi) { uint32_t a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4); return (u64)a | ((u64)b << 32); }
+SC_DEV f2 unpk(u64 v) { uint32_t a = (uint32_t)v, b = (uint32_t)(v >> 32); f2 r; memcpy(&r.x, &a, 4); memcpy(&r.y, &b, 4); return r; }
+SC_DEV u64 ffma2(u64 a, u64 b, u64 c) { f2 x = unpk(a), y = unpk(b), z = unpk(c); return pk(fmaf(x.x, y.x, z.x), fmaf(x.y, y.y, z.y)); }
+SC_DEV u64 fmul2(u64 a, u64 b) { f2 x = unpk(a), y = unpk(b); return pk(x.x * y.x, x.y * y.y); }
+SC_DEV u64 fadd2(u64 a, u64 b) { f2 x = unpk(a), y = unpk(b); return pk(x.x + y.x, x.y + y.y); }
+SC_DEV u64 fsub2(u64 a, u64 b) { f2 x = unpk(a), y = unpk(b); return pk(x.x - y.x, x.y - y.y); }
+SC_DEV uint32_t f2_to_h2(float lo, float hi) {
+    _Float16 a = (_Float16)lo, b = (_Float16)hi;
+    uint16_t ua, ub; memcpy(&ua, &a, 2); memcpy(&ub, &b, 2);
+    return (uint32_t)ua | ((uint32_t)ub << 16);
+}
+SC_DEV uint32_t fbits(float v) { uint32_t u; memcpy(&u, &v, 4); return u; }
+SC_DEV float bitsf(uint32_t u) { float v; memcpy(&v, &u, 4); return v; }
+SC_DEV float ldg1(const float* p) { return *p; }
+SC_DEV void st_u2(uint8_t* p, uint32_t a, uint32_t b) { memcpy(p, &a, 4); memcpy(p + 4, &b, 4); }
+#else
+typedef float2 f2;
+typedef float4 f4;
+SC_DEV u64 pk(float lo, float hi) {
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
+    return d;
+}
+SC_DEV f2 unpk(u64 v) {
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+    return make_float2(__uint_as_float(lo), __uint_as_float(hi));
+}
+// packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): one issue slot per TWO fp32 operations
+SC_DEV u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+SC_DEV u64 fmul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+SC_DEV u64 fadd2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+SC_DEV u64 fsub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+SC_DEV uint32_t f2_to_h2(float lo, float hi) { __half2 h = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+SC_DEV uint32_t fbits(float v) { return __float_as_uint(v); }
+SC_DEV float bitsf(uint32_t u) { return __uint_as_float(u); }
+SC_DEV float ldg1(const float* p) { return __ldg(p); }
+SC_DEV void st_u2(uint8_t* p, uint32_t a, uint32_t b) { *reinterpret_cast<uint2*>(p) = make_uint2(a, b); }
+#endif
+
+SC_DEV int imin(int a, int b) { return a < b ? a : b; }
+SC_DEV int imax(int a, int b) { return a > b ? a : b; }
+SC_DEV int iclamp(int v, int lo, int hi) { return imin(imax(v, lo), hi); }
+
+struct F4 { u64 lo, hi; };   // four floats as two packed pairs (the registers of a float4)
+SC_DEV F4 as_f4(const f4 v) { F4 r; r.lo = pk(v.x, v.y); r.hi = pk(v.z, v.w); return r; }
+SC_DEV f4 to_f4(const F4 v) { const f2 a = unpk(v.lo), b = unpk(v.hi); f4 r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y; return r; }
+SC_DEV void fma4p(F4& acc, const F4 w, const F4 v) { acc.lo = ffma2(w.lo, v.lo, acc.lo); acc.hi = ffma2(w.hi, v.hi, acc.hi); }
+SC_DEV void fma4s(F4& acc, const u64 w2, const F4 v) { acc.lo = ffma2(w2, v.lo, acc.lo); acc.hi = ffma2(w2, v.hi, acc.hi); }
+
+// clamp(max(v, 0.2 v), +-lim) on a pair: lrelu_agc with the gain already folded into v (v = gain * pre-activation)
+SC_DEV u64 act_pair(u64 v, float lim) {
+    const f2 a = unpk(v), b = unpk(fmul2(v, pk(kAlpha, kAlpha)));
+    return pk(fminf(fmaxf(fmaxf(a.x, b.x), -lim), lim), fminf(fmaxf(fmaxf(a.y, b.y), -lim), lim));
+}
+// fp32 pair s (|s| <= 16384) -> fp16x2 hi and lo with hi + lo ~= s to 22 bits.  hi = s with the low 13 mantissa bits
+// cleared (exactly representable in fp16), lo = fp16(s - hi).
+SC_DEV void split_pack2(const f2 s, uint32_t& hi, uint32_t& lo) {
+    const float hx = bitsf(fbits(s.x) & 0xFFFFE000u), hy = bitsf(fbits(s.y) & 0xFFFFE000u);
+    const f2 d = unpk(fsub2(pk(s.x, s.y), pk(hx, hy)));
+    hi = f2_to_h2(hx, hy);
+    lo = f2_to_h2(d.x, d.y);
+}
+// byte offset of (row m, 16-byte chunk j of the 128-byte K row) in a SWIZZLE_128B K-major operand plane
+SC_DEV uint32_t a_off(int m, uint32_t j) { return (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u + ((j ^ (uint32_t)(m & 7)) << 4); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Depthwise 3x3 + bias + lrelu_agc on one 32-channel chunk -> its half of the A operand K block (fp16 hi/lo).
+// The taps / bias carry S = kSplit * sqrt(2):  S * clamp(lrelu(v) * sqrt2, +-256) == clamp(max(v', .2 v'), +-256 kSplit).
+// Worker = (column, 4-channel vector); it slides a 3x3 window down the TH rows: 3 LDS.128 per output row, all
+// offsets compile-time.  SeparableConv2d.conv1 + activation, migan_inference.py:155-157.
+//   sin   IN stage (float4 units)      w9/bias  [9][cin] / [cin] tap tables (shared memory or global)
+//   g     which 32-channel half of the 64-channel K block this chunk is (0/1);  cg0 = first channel of the chunk
+// ---------------------------------------------------------------------------------------------------------------
+template <int TN, int TH, int TW>
+SC_DEV void prologue_chunk(const f4* __restrict__ sin, uint8_t* __restrict__ a_hi, uint8_t* __restrict__ a_lo,
+                           const float* __restrict__ w9, const float* __restrict__ bias, int cin, int cg0, int g, int tg) {
+    constexpr int NCOLS = TN * TW;
+    constexpr int ROW_F4 = (TW + 2) * 8;                   // float4 per halo'd input row (8 float4 / pixel)
+#pragma unroll
+    for (int rep = 0; rep < (NCOLS * 8 + 127) / 128; ++rep) {
+        const int item = tg + rep * 128;
+        const int cvec = item & 7, colidx = item >> 3;
+        const int col = (colidx & 3) * (NCOLS >> 2) + (colidx >> 2);   // spreads a warp over 4 distinct swizzle rows
+        const int img_l = col / TW, x = col % TW;
+        const int cg = cg0 + cvec * 4;
+        F4 w[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w[t] = as_f4(*reinterpret_cast<const f4*>(w9 + t * cin + cg));
+        const F4 bv = as_f4(*reinterpret_cast<const f4*>(bias + cg));
+        const f4* base = sin + (img_l * (TH + 2) * (TW + 2) + x) * 8 + cvec;
+        const uint32_t jchunk = (uint32_t)(g * 4 + (cvec >> 1));
+        const uint32_t sub = (uint32_t)(cvec & 1) * 8;
+        // Two output rows per step: four independent accumulation chains, loads of both rows issued up front.
+        F4 r0[3], r1[3], r2[3], r3[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { r0[d] = as_f4(base[d * 8]); r1[d] = as_f4(base[ROW_F4 + d * 8]); }
+#pragma unroll
+        for (int y = 0; y < TH; y += 2) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { r2[d] = as_f4(base[(y + 2) * ROW_F4 + d * 8]); r3[d] = as_f4(base[(y + 3) * ROW_F4 + d * 8]); }
+            F4 a = bv, b = bv;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                fma4p(a, w[d], r0[d]);     fma4p(b, w[d], r1[d]);
+                fma4p(a, w[3 + d], r1[d]); fma4p(b, w[3 + d], r2[d]);
+                fma4p(a, w[6 + d], r2[d]); fma4p(b, w[6 + d], r3[d]);
+            }
+            constexpr float kLim = kClamp * kSplit;
+            uint32_t hi0x, hi0y, lo0x, lo0y, hi1x, hi1y, lo1x, lo1y;
+            split_pack2(unpk(act_pair(a.lo, kLim)), hi0x, lo0x);
+            split_pack2(unpk(act_pair(b.lo, kLim)), hi1x, lo1x);
+            split_pack2(unpk(act_pair(a.hi, kLim)), hi0y, lo0y);
+            split_pack2(unpk(act_pair(b.hi, kLim)), hi1y, lo1y);
+            const int m0 = (img_l * TH + y) * TW + x, m1 = m0 + TW;      // rows of the M tile
+            const uint32_t off0 = a_off(m0, jchunk) + sub, off1 = a_off(m1, jchunk) + sub;
+            st_u2(a_hi + off0, hi0x, hi0y);
+            st_u2(a_lo + off0, lo0x, lo0y);
+            st_u2(a_hi + off1, hi1x, hi1y);
+            st_u2(a_lo + off1, lo1x, lo1y);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { r0[d] = r2[d]; r1[d] = r3[d]; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// UP pre-stage: builds the depthwise conv's input IN[r][c] in place from the PREVIOUS layer's raw 1x1 output:
+//   x = lrelu_agc( Upsample2d(t) + noise ) + skip          migan_inference.py:98-103, :165-169, :304-305
+// Upsample2d = zero insertion + pad(2,1,2,1) + 4x4 FIR, i.e. the polyphase form
+//   out[2i + a][2j + b] = sum_{u,v in {0,1}} f[a + 2u][b + 2v] * t[i - 1 + a + u][j - 1 + b + v]      (t = 0 outside)
+// IN arrives holding the skip tensor (encoder feature, zero outside the image); pixels outside the image must stay
+// ZERO (they are the depthwise conv's zero padding), not act(noise).
+// `f` = the 16 taps * sqrt(2) (channel-uniform: checked on the host), NZ = noise * sqrt(2).
+// Worker item = (cell row ci 0..5, cell-column pair p 0..4, channel vector): 2 x 4 output pixels from a 3 x 4 window
+// of t; 240 items per chunk.  Cell (ci, cj) <-> low-res pixel (y0/2 - 1 + ci, x0/2 - 1 + cj) covers IN rows
+// 2ci-1, 2ci and cols 2cj-1, 2cj.
+// ---------------------------------------------------------------------------------------------------------------
+struct UpTaps { float f[16]; };
+
+SC_DEV void prestage_up(f4* __restrict__ in, const f4* __restrict__ ta, const float* __restrict__ nz, const UpTaps& taps,
+                        int y0, int x0, int R, int has_noise, int tg) {
+    const int cvec = tg & 7;
+#pragma unroll 1
+    for (int item = tg; item < 240; item += 128) {
+        const int q = item >> 3;
+        const int ci = q / 5, p = q - ci * 5;
+        F4 T[3][4];
+#pragma unroll
+        for (int dr = 0; dr < 3; ++dr) {
+            const int tr = iclamp(ci - 1 + dr, 0, 5);
+#pragma unroll
+            for (int dc = 0; dc < 4; ++dc) {
+                const int tc = iclamp(2 * p - 1 + dc, 0, 9);
+                T[dr][dc] = as_f4(ta[(tr * 10 + tc) * 8 + cvec]);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int r = 2 * ci - 1 + a;                  // IN row; -1 (ci = 0, a = 0) and 10 (ci = 5, a = 1) do not exist
+            const bool rok = (r >= 0) && (r <= 9);
+            const int rc = iclamp(r, 0, 9);
+            const int Y = y0 - 1 + rc;
+            f4 nzv; nzv.x = nzv.y = nzv.z = nzv.w = 0.f;
+            if (has_noise) nzv = *reinterpret_cast<const f4*>(nz + rc * 20 + 4 * p);   // noise of cols 4p-1 .. 4p+2
+            const float nzs[4] = {nzv.x, nzv.y, nzv.z, nzv.w};
+#pragma unroll
+            for (int b4 = 0; b4 < 4; ++b4) {
+                const int c = 4 * p - 1 + b4;              // IN col; -1 (p = 0) and 18 (p = 4) do not exist
+                const bool ok = rok && (c >= 0) && (c <= 17);
+                const int cc = iclamp(c, 0, 17);
+                const int X = x0 - 1 + cc;
+                const int b = b4 & 1, dc0 = (b4 >> 1) + b;  // window column of tap v = 0
+                F4 acc; acc.lo = acc.hi = pk(nzs[b4], nzs[b4]);
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        const float fv = taps.f[(a + 2 * u) * 4 + (b + 2 * v)];
+                        fma4s(acc, pk(fv, fv), T[a + u][dc0 + v]);
+                    }
+                const bool inside = (Y >= 0) && (Y < R) && (X >= 0) && (X < R);
+                f4* px = in + (rc * 18 + cc) * 8 + cvec;
+                const F4 sk = as_f4(*px);
+                F4 o;
+                o.lo = fadd2(act_pair(acc.lo, kClamp), sk.lo);
+                o.hi = fadd2(act_pair(acc.hi, kClamp), sk.hi);
+                if (!inside) { o.lo = 0ull; o.hi = 0ull; }
+                if (ok) *px = to_f4(o);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// STEM pre-stage: IN[r][c][ch] = lrelu_agc( fromrgb(x)[ch] + b[ch] ) for the chunk's 32 channels (zero outside the
+// image): EncoderBlock.fromrgb + activation, migan_inference.py:193-196, recomputed on the halo so the 64-channel
+// stem tensor never exists in HBM.  ws = [C0][4] weights * sqrt2, bs = [C0] bias * sqrt2 (shared-memory table).
+// Worker item = (pixel of the 10 x 18 window, channel vector): 1440 items per chunk.
+// ---------------------------------------------------------------------------------------------------------------
+SC_DEV void prestage_stem(f4* __restrict__ in, const float* __restrict__ xa, const float* __restrict__ ws,
+                          const float* __restrict__ bs, int cg0, int y0, int x0, int R, int tg) {
+    const int cvec = tg & 7;
+    const int ch = cg0 + cvec * 4;
+    const f4 w0 = *reinterpret_cast<const f4*>(ws + (ch + 0) * 4), w1 = *reinterpret_cast<const f4*>(ws + (ch + 1) * 4);
+    const f4 w2 = *reinterpret_cast<const f4*>(ws + (ch + 2) * 4), w3 = *reinterpret_cast<const f4*>(ws + (ch + 3) * 4);
+    const f4 bv = *reinterpret_cast<const f4*>(bs + ch);
+    const u64 wl[4] = {pk(w0.x, w1.x), pk(w0.y, w1.y), pk(w0.z, w1.z), pk(w0.w, w1.w)};   // (ch, ch+1) x input plane
+    const u64 wh[4] = {pk(w2.x, w3.x), pk(w2.y, w3.y), pk(w2.z, w3.z), pk(w2.w, w3.w)};   // (ch+2, ch+3)
+    const u64 bl = pk(bv.x, bv.y), bh = pk(bv.z, bv.w);
+#pragma unroll 4
+    for (int k = 0; k < 12; ++k) {
+        const int px = (tg >> 3) + 16 * k;
+        if (px >= 180) break;
+        const int r = px / 18, c = px - r * 18;
+        const int Y = y0 - 1 + r, X = x0 - 1 + c;
+        u64 lo = bl, hi = bh;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float xv = xa[i * 200 + r * 20 + c + 1];
+            const u64 x2 = pk(xv, xv);
+            lo = ffma2(x2, wl[i], lo);
+            hi = ffma2(x2, wh[i], hi);
+        }
+        F4 o;
+        o.lo = act_pair(lo, kClamp);
+        o.hi = act_pair(hi, kClamp);
+        if (!((Y >= 0) && (Y < R) && (X >= 0) && (X < R))) { o.lo = 0ull; o.hi = 0ull; }
+        in[px * 8 + cvec] = to_f4(o);
+    }
+}
+
+}  // namespace stages
+}  // namespace migan

@@ -101,6 +101,9 @@ class _Engine:
             raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
             off = (-raw.data_ptr()) % 1024
             ws = raw[off:off + nbytes]
+            if any(k[0] != n for k in self.workspaces):
+                # copies enqueued by forward_host(wait=False) may still be using a staging area that is about to be released
+                _abi.check(self.lib.migan_host_wait(self.handle))
             self.workspaces = {k: v for k, v in self.workspaces.items() if k[0] == n}  # keep one batch size
             self.workspaces[key] = ws
         return ws
@@ -139,6 +142,7 @@ class Generator(nn.Module):
     def __getstate__(self):  # engines hold C handles: never pickled / deep-copied
         state = self.__dict__.copy()
         state["_engines"] = {}
+        state["_state_tensors"] = None
         return state
 
     # -- plumbing ---------------------------------------------------------------------
@@ -149,7 +153,22 @@ class Generator(nn.Module):
         return _abi.PATHS[name]
 
     def _state_version(self):
-        return tuple((t._version, t.data_ptr()) for t in self.state_dict(keep_vars=True).values())
+        # Cheap per-call check that the uploaded weights are still current: the tensor list is collected once (and again
+        # after load_state_dict / .to() / .cuda(), which may replace tensors) and each call only sums version counters.
+        tensors = self.__dict__.get("_state_tensors")
+        if tensors is None:
+            tensors = tuple(self.state_dict(keep_vars=True).values())
+            self.__dict__["_state_tensors"] = tensors
+            self.__dict__["_state_ptrs"] = tuple(t.data_ptr() for t in tensors)
+        return (sum(t._version for t in tensors), self.__dict__["_state_ptrs"])
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__["_state_tensors"] = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__["_state_tensors"] = None
+        return super().load_state_dict(*args, **kwargs)
 
     def _engine(self, device: torch.device) -> _Engine:
         eng = self._engines.get(device)
@@ -204,11 +223,15 @@ class Generator(nn.Module):
             raise RuntimeError("forward_host expects a CPU float32 tensor of shape [N, 4, %d, %d]" % (r, r))
         x_host = x_host.contiguous()
         n = x_host.shape[0]
+        if n == 0:
+            raise RuntimeError("empty batch")
         device = next(self.parameters()).device
         if device.type != "cuda":
             raise RuntimeError("module parameters must be on a CUDA device (call .to('cuda')); there is no CPU path")
         if out is None:
             out = torch.empty((n, 3, r, r), dtype=torch.float32, pin_memory=True)
+        if out.is_cuda or out.dtype != torch.float32 or tuple(out.shape) != (n, 3, r, r) or not out.is_contiguous():
+            raise RuntimeError("out must be a contiguous CPU float32 tensor of shape [N, 3, %d, %d]" % (r, r))
         with torch.cuda.device(device):
             eng = self._engine(device)
             ws = eng.workspace(n, host_staging=True)
@@ -247,6 +270,8 @@ class Generator(nn.Module):
                 raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
                 off = (-raw.data_ptr()) % 1024
                 ws = raw[off:off + nbytes]
+                if any(k[0] != n for k in eng.workspaces):
+                    _abi.check(eng.lib.migan_host_wait(eng.handle))
                 eng.workspaces = {k: v for k, v in eng.workspaces.items() if k[0] == n}
                 eng.workspaces[(n, "u8")] = ws
             stream = torch.cuda.current_stream(device).cuda_stream
