@@ -845,8 +845,9 @@ int run_step(migan_ctx* ctx, Step& s, const float* x, float* y, cudaStream_t st)
             e = migan::launch_add(out, s.aux, (int64_t)s.n * s.H * s.W * s.C, st);
             break;
     }
-    if (e != cudaSuccess) return fail(MIGAN_ERR_CUDA, "kernel launch (step kind %d, %s) failed: %s", (int)s.kind,
-                                      s.tap.c_str(), cudaGetErrorString(e));
+    if (e != cudaSuccess)   // asynchronous failures of EARLIER launches surface here too: the pipeline-timeout record names the wait
+        return fail(MIGAN_ERR_CUDA, "kernel launch (step %s) failed: %s [tcgen05 pipeline timeout record 0x%x]", s.label.c_str(),
+                    cudaGetErrorString(e), (unsigned)migan::sepconv_tc_timeout_record(ctx->device));
     ctx->last_launches++;
     if (ctx->tap_dst && !s.tap.empty() && s.tap == ctx->tap_name) {
         const float* src = (s.tap_flags & PTR_Y) ? y : s.tap_src;

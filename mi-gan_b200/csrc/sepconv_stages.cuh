@@ -11,8 +11,11 @@
 // Stage layouts (one 32-channel chunk of one 8 x 16 output tile at origin (y0, x0), TMA boxes, no swizzle):
 //   IN   [10 rows][18 cols][32 ch] fp32   rows y0-1 .. y0+8, cols x0-1 .. x0+16: the depthwise conv's input + halo
 //   T    [ 6 rows][10 cols][32 ch] fp32   UP: raw 1x1 output of the up-sampling layer, rows y0/2-1 .. y0/2+4
-//   NZ   [10 rows][20 cols]        fp32   UP: noise map rows y0-1 .. y0+8, cols x0-2 .. x0+17 (16-byte rows)
-//   XA   [4 planes][10 rows][20 cols] fp32 STEM: the generator input x (NCHW planes), same window as NZ
+//   NZ   [10 rows][24 cols]        fp32   UP: noise map rows y0-1 .. y0+8, cols x0-4 .. x0+19
+//   XA   [4 planes][10 rows][24 cols] fp32 STEM: the generator input x (NCHW planes), same window as NZ
+//        (W is the innermost tensor-map dimension of these two: the box starts 4 elements = 16 bytes left of the tile.
+//         A box starting at x0-2, i.e. 8 bytes off a 16-byte boundary, faults the TMA unit on B200 -- measured: illegal
+//         instruction -- so the window is 24 wide and the 18 columns used sit at indices 3 .. 20.)
 //   DIN  [20 rows][36 cols][16 ch] fp32   DOWN: input rows 2*y0-2 .. 2*y0+17, cols 2*x0-2 .. 2*x0+33 (16-ch chunk)
 // A operand (one K block of 64 channels, M = 128 pixel rows): fp16 hi and lo planes, UMMA K-major SWIZZLE_128B:
 //   byte(m, k) = (m >> 3) * 1024 + (m & 7) * 128 + (((k >> 3) ^ (m & 7)) << 4) + (k & 7) * 2
@@ -36,6 +39,8 @@ constexpr float kAlpha = 0.2f;                 // lrelu_agc (migan_inference.py:
 constexpr float kGain = 1.41421356237309515f;
 constexpr float kClamp = 256.0f;
 constexpr float kSplit = 64.0f;                // power-of-two scale of the fp16 hi/lo split (common.cuh kActSplitScale)
+constexpr int kAuxW = 24;                      // row length of the NZ / XA windows
+constexpr int kAuxLeft = 4;                    // the windows start at column x0 - kAuxLeft; IN column c <-> window column c + 3
 
 typedef unsigned long long u64;
 
@@ -206,7 +211,11 @@ SC_DEV void prestage_up(f4* __restrict__ in, const f4* __restrict__ ta, const fl
             const int rc = iclamp(r, 0, 9);
             const int Y = y0 - 1 + rc;
             f4 nzv; nzv.x = nzv.y = nzv.z = nzv.w = 0.f;
-            if (has_noise) nzv = *reinterpret_cast<const f4*>(nz + rc * 20 + 4 * p);   // noise of cols 4p-1 .. 4p+2
+            if (has_noise) {                               // noise of IN cols 4p-1 .. 4p+2 = window cols 4p+2 .. 4p+5 (8-byte aligned)
+                const f2 n01 = *reinterpret_cast<const f2*>(nz + rc * kAuxW + 4 * p + kAuxLeft - 2);
+                const f2 n23 = *reinterpret_cast<const f2*>(nz + rc * kAuxW + 4 * p + kAuxLeft);
+                nzv.x = n01.x; nzv.y = n01.y; nzv.z = n23.x; nzv.w = n23.y;
+            }
             const float nzs[4] = {nzv.x, nzv.y, nzv.z, nzv.w};
 #pragma unroll
             for (int b4 = 0; b4 < 4; ++b4) {
@@ -261,7 +270,7 @@ SC_DEV void prestage_stem(f4* __restrict__ in, const float* __restrict__ xa, con
         u64 lo = bl, hi = bh;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float xv = xa[i * 200 + r * 20 + c + 1];
+            const float xv = xa[i * (10 * kAuxW) + r * kAuxW + c + kAuxLeft - 1];
             const u64 x2 = pk(xv, xv);
             lo = ffma2(x2, wl[i], lo);
             hi = ffma2(x2, wh[i], hi);

@@ -364,12 +364,12 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                             const uint32_t dst = smem_base + p.off_in + s * p.in_stage_stride;
                             const int c0 = kb * kKBlock + g * kChunkC;
                             if (p.source == SEPCONV_SRC_STEM) {
-                                tma_load_4d(dst + p.off_aux, &p.map_aux, full_in(s), tc.x0 - 2, tc.y0 - 1, 0, tc.n0);
+                                tma_load_4d(dst + p.off_aux, &p.map_aux, full_in(s), tc.x0 - kAuxLeft, tc.y0 - 1, 0, tc.n0);
                             } else {
                                 tma_load_4d(dst, &p.map_in, full_in(s), c0, tc.x0 - 1, tc.y0 - 1, tc.n0);
                                 if (p.source == SEPCONV_SRC_UP) {
                                     tma_load_4d(dst + p.off_t, &p.map_t, full_in(s), c0, (tc.x0 >> 1) - 1, (tc.y0 >> 1) - 1, tc.n0);
-                                    if (p.up_has_noise) tma_load_2d(dst + p.off_aux, &p.map_aux, full_in(s), tc.x0 - 2, tc.y0 - 1);
+                                    if (p.up_has_noise) tma_load_2d(dst + p.off_aux, &p.map_aux, full_in(s), tc.x0 - kAuxLeft, tc.y0 - 1);
                                 }
                             }
                         }
@@ -689,7 +689,7 @@ const char* encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const v
 const char* encode_x_map(CUtensorMap* m, const void* x, int n, int res) {
     const uint64_t dims[4] = {(uint64_t)res, (uint64_t)res, 4, (uint64_t)n};
     const uint64_t str[3] = {(uint64_t)res * 4, (uint64_t)res * res * 4, (uint64_t)res * res * 16};
-    const uint32_t box[4] = {20, 10, 4, 1};
+    const uint32_t box[4] = {(uint32_t)kAuxW, 10, 4, 1};
     return encode_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
@@ -769,13 +769,13 @@ const char* sepconv_tc_plan_ex(SepconvTcArgs* args, const SepconvTcDesc& d) {
     if (d.source == SEPCONV_SRC_UP) {
         p.off_t = in_chunk_bytes;                 // 23040: 128-byte aligned
         p.off_aux = p.off_t + 6 * 10 * kChunkC * 4;
-        stage_bytes = p.off_aux + 10 * 20 * 4;
-        p.in_tx_bytes = in_chunk_bytes + 6 * 10 * kChunkC * 4 + (p.up_has_noise ? 10 * 20 * 4 : 0);
+        stage_bytes = p.off_aux + 10 * kAuxW * 4;
+        p.in_tx_bytes = in_chunk_bytes + 6 * 10 * kChunkC * 4 + (p.up_has_noise ? 10 * kAuxW * 4 : 0);
         memcpy(p.up_taps.f, d.up_taps, sizeof(p.up_taps.f));
     } else if (d.source == SEPCONV_SRC_STEM) {
         p.off_aux = in_chunk_bytes;
-        stage_bytes = p.off_aux + 4 * 10 * 20 * 4;
-        p.in_tx_bytes = 4 * 10 * 20 * 4;
+        stage_bytes = p.off_aux + 4 * 10 * kAuxW * 4;
+        p.in_tx_bytes = 4 * 10 * kAuxW * 4;
         p.stem_w = d.stem_w; p.stem_b = d.stem_b;
     }
     p.in_stage_stride = (stage_bytes + 1023u) & ~1023u;
@@ -859,7 +859,7 @@ const char* sepconv_tc_plan_ex(SepconvTcArgs* args, const SepconvTcDesc& d) {
         if (p.up_has_noise) {
             const uint64_t nd[2] = {(uint64_t)res, (uint64_t)res};
             const uint64_t ns[1] = {(uint64_t)res * 4};
-            const uint32_t nb[2] = {20, 10};
+            const uint32_t nb[2] = {(uint32_t)kAuxW, 10};
             if ((err = encode_map(&p.map_aux, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.up_noise, nd, ns, nb, CU_TENSOR_MAP_SWIZZLE_NONE))) return err;
         }
     }

@@ -93,7 +93,7 @@ def test_prestage_up_matches_oracle(lib, y0, x0, has_noise):
     for cg0 in (0, 32):
         in_stage = tma_box(skip_hwc, (cg0, x0 - 1, y0 - 1), (32, 18, 10)).copy()
         t_area = tma_box(t_hwc, (cg0, x0 // 2 - 1, y0 // 2 - 1), (32, 10, 6)).copy()
-        nz_area = tma_box(nz, (x0 - 2, y0 - 1), (20, 10)).copy()
+        nz_area = tma_box(nz, (x0 - 4, y0 - 1), (24, 10)).copy()
         lib.emul_prestage_up(ptr(in_stage), ptr(t_area), ptr(nz_area), ptr(taps16), y0, x0, R, has_noise)
         ref = want[y0:y0 + 10, x0:x0 + 18, cg0:cg0 + 32]
         err = np.abs(in_stage - ref).max()
@@ -124,7 +124,7 @@ def test_prestage_up_clamps(lib):
     skip_hwc = np.ascontiguousarray(skip[0].permute(1, 2, 0).numpy())
     in_stage = tma_box(skip_hwc, (0, x0 - 1, y0 - 1), (32, 18, 10)).copy()
     t_area = tma_box(t_hwc, (0, x0 // 2 - 1, y0 // 2 - 1), (32, 10, 6)).copy()
-    nz_area = np.zeros((10, 20), np.float32)
+    nz_area = np.zeros((10, 24), np.float32)
     taps16 = np.ascontiguousarray((taps.numpy().reshape(16) * SQRT2).astype(np.float32))
     lib.emul_prestage_up(ptr(in_stage), ptr(t_area), ptr(nz_area), ptr(taps16), y0, x0, R, 0)
     assert np.abs(in_stage - want[y0:y0 + 10, x0:x0 + 18, :32]).max() < 1e-3
@@ -146,7 +146,7 @@ def test_prestage_stem_matches_oracle(lib, y0, x0):
     xn = np.ascontiguousarray(x[0].numpy())                                   # [4][R][R]
     for cg0 in (0, 32):
         in_stage = np.full((10, 18, 32), np.nan, np.float32)                  # the stage is NOT pre-filled in this mode
-        x_area = tma_box(xn, (x0 - 2, y0 - 1, 0), (20, 10, 4)).copy()
+        x_area = tma_box(xn, (x0 - 4, y0 - 1, 0), (24, 10, 4)).copy()
         lib.emul_prestage_stem(ptr(in_stage), ptr(x_area), ptr(ws), ptr(bs), cg0, y0, x0, R)
         ref = want[y0:y0 + 10, x0:x0 + 18, cg0:cg0 + 32]
         assert np.isfinite(in_stage).all()

@@ -30,8 +30,14 @@ def main():
     taps = {}
     want = O.generator_forward(sd, x, a.res, taps=taps)
     xd = x.to(dev)
-    y = g(xd)
-    torch.cuda.synchronize()
+    try:
+        y = g(xd)
+        torch.cuda.synchronize()
+    except Exception as e:  # a trapped pipeline wait leaves a host-mapped record naming the barrier
+        from migan_b200 import _abi
+        print("[diag] FAILED: %s" % str(e).splitlines()[-1])
+        print("[diag] tcgen05 timeout record: 0x%x" % (_abi.load().migan_debug_tc_timeout(0) & 0xFFFFFFFF), flush=True)
+        sys.exit(3)
     d = (y.cpu() - want).abs()
     print("[diag] path=%s R=%d N=%d launches=%d  FINAL max-abs=%.3e mean-abs=%.3e |y|max=%.3f"
           % (a.path, a.res, a.n, g.last_launch_count(), float(d.max()), float(d.mean()), float(want.abs().max())), flush=True)
