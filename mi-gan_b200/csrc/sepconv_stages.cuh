@@ -42,17 +42,18 @@ constexpr float kSplit = 64.0f;                // power-of-two scale of the fp16
 constexpr int kAuxW = 24;                      // row length of the NZ / XA windows
 constexpr int kAuxLeft = 4;                    // the windows start at column x0 - kAuxLeft; IN column c <-> window column c + 3
 
-typedef unsigned long long u64;
-
+// A pair of fp32 values processed by ONE packed instruction (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot per two fp32
+// operations).  On the device P2 is float2 and the arithmetic goes through the sm_100 intrinsics (__ffma2_rn ...): the
+// compiler then allocates the even-aligned register pairs itself.  (Inline-asm "mov.b64 {lo, hi}" wrappers cost one
+// register move per packed operand: 15-19 % of all instructions the kernel executed in the round-2 ncu source view.)
 #ifdef MIGAN_EMULATE
-struct f2 { float x, y; };
+struct P2 { float x, y; };
+typedef P2 f2;
 struct alignas(16) f4 { float x, y, z, w; };
-SC_DEV u64 pk(float lo, float hi) { uint32_t a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4); return (u64)a | ((u64)b << 32); }
-SC_DEV f2 unpk(u64 v) { uint32_t a = (uint32_t)v, b = (uint32_t)(v >> 32); f2 r; memcpy(&r.x, &a, 4); memcpy(&r.y, &b, 4); return r; }
-SC_DEV u64 ffma2(u64 a, u64 b, u64 c) { f2 x = unpk(a), y = unpk(b), z = unpk(c); return pk(fmaf(x.x, y.x, z.x), fmaf(x.y, y.y, z.y)); }
-SC_DEV u64 fmul2(u64 a, u64 b) { f2 x = unpk(a), y = unpk(b); return pk(x.x * y.x, x.y * y.y); }
-SC_DEV u64 fadd2(u64 a, u64 b) { f2 x = unpk(a), y = unpk(b); return pk(x.x + y.x, x.y + y.y); }
-SC_DEV u64 fsub2(u64 a, u64 b) { f2 x = unpk(a), y = unpk(b); return pk(x.x - y.x, x.y - y.y); }
+SC_DEV P2 pk(float lo, float hi) { P2 r; r.x = lo; r.y = hi; return r; }
+SC_DEV P2 ffma2(P2 a, P2 b, P2 c) { return pk(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+SC_DEV P2 fmul2(P2 a, P2 b) { return pk(a.x * b.x, a.y * b.y); }
+SC_DEV P2 fadd2(P2 a, P2 b) { return pk(a.x + b.x, a.y + b.y); }
 SC_DEV uint32_t f2_to_h2(float lo, float hi) {
     _Float16 a = (_Float16)lo, b = (_Float16)hi;
     uint16_t ua, ub; memcpy(&ua, &a, 2); memcpy(&ub, &b, 2);
@@ -62,30 +63,26 @@ SC_DEV uint32_t fbits(float v) { uint32_t u; memcpy(&u, &v, 4); return u; }
 SC_DEV float bitsf(uint32_t u) { float v; memcpy(&v, &u, 4); return v; }
 SC_DEV float ldg1(const float* p) { return *p; }
 SC_DEV void st_u2(uint8_t* p, uint32_t a, uint32_t b) { memcpy(p, &a, 4); memcpy(p + 4, &b, 4); }
+SC_DEV float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 #else
+typedef float2 P2;
 typedef float2 f2;
 typedef float4 f4;
-SC_DEV u64 pk(float lo, float hi) {
-    u64 d;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
-    return d;
-}
-SC_DEV f2 unpk(u64 v) {
-    uint32_t lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-    return make_float2(__uint_as_float(lo), __uint_as_float(hi));
-}
-// packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): one issue slot per TWO fp32 operations
-SC_DEV u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-SC_DEV u64 fmul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-SC_DEV u64 fadd2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-SC_DEV u64 fsub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+SC_DEV P2 pk(float lo, float hi) { return make_float2(lo, hi); }
+SC_DEV P2 ffma2(P2 a, P2 b, P2 c) { return __ffma2_rn(a, b, c); }
+SC_DEV P2 fmul2(P2 a, P2 b) { return __fmul2_rn(a, b); }
+SC_DEV P2 fadd2(P2 a, P2 b) { return __fadd2_rn(a, b); }
 SC_DEV uint32_t f2_to_h2(float lo, float hi) { __half2 h = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
 SC_DEV uint32_t fbits(float v) { return __float_as_uint(v); }
 SC_DEV float bitsf(uint32_t u) { return __uint_as_float(u); }
 SC_DEV float ldg1(const float* p) { return __ldg(p); }
 SC_DEV void st_u2(uint8_t* p, uint32_t a, uint32_t b) { *reinterpret_cast<uint2*>(p) = make_uint2(a, b); }
+SC_DEV float fmax3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }   // FMNMX3
 #endif
+SC_DEV P2 unpk(P2 v) { return v; }
+SC_DEV P2 fsub2(P2 a, P2 b) { return ffma2(b, pk(-1.0f, -1.0f), a); }     // a - b, exact (one FFMA2)
+SC_DEV P2 p2zero() { return pk(0.0f, 0.0f); }
+typedef P2 u64;   // historical name of the packed pair in this file
 
 SC_DEV int imin(int a, int b) { return a < b ? a : b; }
 SC_DEV int imax(int a, int b) { return a > b ? a : b; }
@@ -93,20 +90,20 @@ SC_DEV int iclamp(int v, int lo, int hi) { return imin(imax(v, lo), hi); }
 
 struct F4 { u64 lo, hi; };   // four floats as two packed pairs (the registers of a float4)
 SC_DEV F4 as_f4(const f4 v) { F4 r; r.lo = pk(v.x, v.y); r.hi = pk(v.z, v.w); return r; }
-SC_DEV f4 to_f4(const F4 v) { const f2 a = unpk(v.lo), b = unpk(v.hi); f4 r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y; return r; }
+SC_DEV f4 to_f4(const F4 v) { f4 r; r.x = v.lo.x; r.y = v.lo.y; r.z = v.hi.x; r.w = v.hi.y; return r; }
 SC_DEV void fma4p(F4& acc, const F4 w, const F4 v) { acc.lo = ffma2(w.lo, v.lo, acc.lo); acc.hi = ffma2(w.hi, v.hi, acc.hi); }
 SC_DEV void fma4s(F4& acc, const u64 w2, const F4 v) { acc.lo = ffma2(w2, v.lo, acc.lo); acc.hi = ffma2(w2, v.hi, acc.hi); }
 
 // clamp(max(v, 0.2 v), +-lim) on a pair: lrelu_agc with the gain already folded into v (v = gain * pre-activation)
-SC_DEV u64 act_pair(u64 v, float lim) {
-    const f2 a = unpk(v), b = unpk(fmul2(v, pk(kAlpha, kAlpha)));
-    return pk(fminf(fmaxf(fmaxf(a.x, b.x), -lim), lim), fminf(fmaxf(fmaxf(a.y, b.y), -lim), lim));
+SC_DEV P2 act_pair(P2 v, float lim) {
+    const P2 b = fmul2(v, pk(kAlpha, kAlpha));
+    return pk(fminf(fmax3(v.x, b.x, -lim), lim), fminf(fmax3(v.y, b.y, -lim), lim));
 }
 // fp32 pair s (|s| <= 16384) -> fp16x2 hi and lo with hi + lo ~= s to 22 bits.  hi = s with the low 13 mantissa bits
 // cleared (exactly representable in fp16), lo = fp16(s - hi).
-SC_DEV void split_pack2(const f2 s, uint32_t& hi, uint32_t& lo) {
+SC_DEV void split_pack2(const P2 s, uint32_t& hi, uint32_t& lo) {
     const float hx = bitsf(fbits(s.x) & 0xFFFFE000u), hy = bitsf(fbits(s.y) & 0xFFFFE000u);
-    const f2 d = unpk(fsub2(pk(s.x, s.y), pk(hx, hy)));
+    const P2 d = fsub2(s, pk(hx, hy));
     hi = f2_to_h2(hx, hy);
     lo = f2_to_h2(d.x, d.y);
 }
@@ -238,7 +235,7 @@ SC_DEV void prestage_up(f4* __restrict__ in, const f4* __restrict__ ta, const fl
                 F4 o;
                 o.lo = fadd2(act_pair(acc.lo, kClamp), sk.lo);
                 o.hi = fadd2(act_pair(acc.hi, kClamp), sk.hi);
-                if (!inside) { o.lo = 0ull; o.hi = 0ull; }
+                if (!inside) { o.lo = p2zero(); o.hi = p2zero(); }
                 if (ok) *px = to_f4(o);
             }
         }
@@ -278,7 +275,7 @@ SC_DEV void prestage_stem(f4* __restrict__ in, const float* __restrict__ xa, con
         F4 o;
         o.lo = act_pair(lo, kClamp);
         o.hi = act_pair(hi, kClamp);
-        if (!((Y >= 0) && (Y < R) && (X >= 0) && (X < R))) { o.lo = 0ull; o.hi = 0ull; }
+        if (!((Y >= 0) && (Y < R) && (X >= 0) && (X < R))) { o.lo = p2zero(); o.hi = p2zero(); }
         in[px * 8 + cvec] = to_f4(o);
     }
 }
