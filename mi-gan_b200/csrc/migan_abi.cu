@@ -727,7 +727,7 @@ struct PlanBuilder {
             const float* img_lo = (img_cur >= 0) ? IMG[img_cur] : nullptr;
             float* img_out = last ? nullptr : IMG[img_next];      // last level: the caller's y (bound at launch)
             const ToRgb& T = c->torgb[i];
-            const bool fuse_rgb = tcp && channels(r) <= 128;
+            const bool fuse_rgb = tcp && channels(r) <= 256;   // all output channels of a pixel tile in one CTA (two N halves at 256)
             // conv1's FIR + noise + activation + skip can be rebuilt in conv2's prologue (the up-sampled tensor then never
             // exists in HBM) when conv2 runs its depthwise stage in the tensor-core kernel with 8 x 16 tiles.
             const SepConv& L1 = c->syn1[i];

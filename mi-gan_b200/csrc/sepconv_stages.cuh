@@ -178,9 +178,12 @@ SC_DEV void prologue_chunk(const f4* __restrict__ sin, uint8_t* __restrict__ a_h
 // IN arrives holding the skip tensor (encoder feature, zero outside the image); pixels outside the image must stay
 // ZERO (they are the depthwise conv's zero padding), not act(noise).
 // `f` = the 16 taps * sqrt(2) (channel-uniform: checked on the host), NZ = noise * sqrt(2).
-// Worker item = (cell row ci 0..5, cell-column pair p 0..4, channel vector): 2 x 4 output pixels from a 3 x 4 window
-// of t; 240 items per chunk.  Cell (ci, cj) <-> low-res pixel (y0/2 - 1 + ci, x0/2 - 1 + cj) covers IN rows
-// 2ci-1, 2ci and cols 2cj-1, 2cj.
+//
+// Decomposition: the tile origin is even, so IN row 2i is the ODD image row 2m-1 and IN row 2i+1 the even row 2m
+// (m = y0/2 + i), and both read the same two low-resolution rows m-1, m (phase a = 1 of cell m-1, phase a = 0 of cell m);
+// likewise for columns.  A worker item is therefore one 2 x 2 block of IN pixels (rows 2i, 2i+1; cols 2j, 2j+1;
+// i < 5, j < 9) computed from the 2 x 2 window T[i..i+1][j..j+1]: the 45 blocks tile the 10 x 18 window exactly -- no
+// clamped indices, no discarded outputs, 4 loads of t per 4 outputs.  360 items (block, 4-channel vector) per chunk.
 // ---------------------------------------------------------------------------------------------------------------
 struct UpTaps { float f[16]; };
 
@@ -188,55 +191,37 @@ SC_DEV void prestage_up(f4* __restrict__ in, const f4* __restrict__ ta, const fl
                         int y0, int x0, int R, int has_noise, int tg) {
     const int cvec = tg & 7;
 #pragma unroll 1
-    for (int item = tg; item < 240; item += 128) {
-        const int q = item >> 3;
-        const int ci = q / 5, p = q - ci * 5;
-        F4 T[3][4];
+    for (int item = tg; item < 360; item += 128) {
+        const int cell = item >> 3;
+        const int i = cell / 9, j = cell - i * 9;
+        const f4* tp = ta + (i * 10 + j) * 8 + cvec;
+        const F4 t00 = as_f4(tp[0]), t01 = as_f4(tp[8]), t10 = as_f4(tp[80]), t11 = as_f4(tp[88]);
+        // rows / columns of the block that lie outside the image (only on border tiles)
+        const bool row_out[2] = {(y0 == 0) && (i == 0), (y0 + 8 == R) && (i == 4)};
+        const bool col_out[2] = {(x0 == 0) && (j == 0), (x0 + 16 == R) && (j == 8)};
+        f4* px0 = in + ((2 * i) * 18 + 2 * j) * 8 + cvec;
+        const float* nzp = nz + (2 * i) * kAuxW + 2 * j + kAuxLeft - 1;
 #pragma unroll
-        for (int dr = 0; dr < 3; ++dr) {
-            const int tr = iclamp(ci - 1 + dr, 0, 5);
+        for (int rr = 0; rr < 2; ++rr) {
+            const int a = 1 - rr;                          // IN row 2i is phase a = 1, row 2i+1 phase a = 0
 #pragma unroll
-            for (int dc = 0; dc < 4; ++dc) {
-                const int tc = iclamp(2 * p - 1 + dc, 0, 9);
-                T[dr][dc] = as_f4(ta[(tr * 10 + tc) * 8 + cvec]);
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            const int r = 2 * ci - 1 + a;                  // IN row; -1 (ci = 0, a = 0) and 10 (ci = 5, a = 1) do not exist
-            const bool rok = (r >= 0) && (r <= 9);
-            const int rc = iclamp(r, 0, 9);
-            const int Y = y0 - 1 + rc;
-            f4 nzv; nzv.x = nzv.y = nzv.z = nzv.w = 0.f;
-            if (has_noise) {                               // noise of IN cols 4p-1 .. 4p+2 = window cols 4p+2 .. 4p+5 (8-byte aligned)
-                const f2 n01 = *reinterpret_cast<const f2*>(nz + rc * kAuxW + 4 * p + kAuxLeft - 2);
-                const f2 n23 = *reinterpret_cast<const f2*>(nz + rc * kAuxW + 4 * p + kAuxLeft);
-                nzv.x = n01.x; nzv.y = n01.y; nzv.z = n23.x; nzv.w = n23.y;
-            }
-            const float nzs[4] = {nzv.x, nzv.y, nzv.z, nzv.w};
-#pragma unroll
-            for (int b4 = 0; b4 < 4; ++b4) {
-                const int c = 4 * p - 1 + b4;              // IN col; -1 (p = 0) and 18 (p = 4) do not exist
-                const bool ok = rok && (c >= 0) && (c <= 17);
-                const int cc = iclamp(c, 0, 17);
-                const int X = x0 - 1 + cc;
-                const int b = b4 & 1, dc0 = (b4 >> 1) + b;  // window column of tap v = 0
-                F4 acc; acc.lo = acc.hi = pk(nzs[b4], nzs[b4]);
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-#pragma unroll
-                    for (int v = 0; v < 2; ++v) {
-                        const float fv = taps.f[(a + 2 * u) * 4 + (b + 2 * v)];
-                        fma4s(acc, pk(fv, fv), T[a + u][dc0 + v]);
-                    }
-                const bool inside = (Y >= 0) && (Y < R) && (X >= 0) && (X < R);
-                f4* px = in + (rc * 18 + cc) * 8 + cvec;
+            for (int cc = 0; cc < 2; ++cc) {
+                const int b = 1 - cc;
+                const float nzv = has_noise ? nzp[rr * kAuxW + cc] : 0.f;
+                F4 acc; acc.lo = acc.hi = pk(nzv, nzv);
+                const float f00 = taps.f[a * 4 + b], f01 = taps.f[a * 4 + b + 2];
+                const float f10 = taps.f[(a + 2) * 4 + b], f11 = taps.f[(a + 2) * 4 + b + 2];
+                fma4s(acc, pk(f00, f00), t00);
+                fma4s(acc, pk(f01, f01), t01);
+                fma4s(acc, pk(f10, f10), t10);
+                fma4s(acc, pk(f11, f11), t11);
+                f4* px = px0 + (rr * 18 + cc) * 8;
                 const F4 sk = as_f4(*px);
                 F4 o;
                 o.lo = fadd2(act_pair(acc.lo, kClamp), sk.lo);
                 o.hi = fadd2(act_pair(acc.hi, kClamp), sk.hi);
-                if (!inside) { o.lo = p2zero(); o.hi = p2zero(); }
-                if (ok) *px = to_f4(o);
+                if (row_out[rr] || col_out[cc]) { o.lo = p2zero(); o.hi = p2zero(); }
+                *px = to_f4(o);
             }
         }
     }
@@ -258,11 +243,12 @@ SC_DEV void prestage_stem(f4* __restrict__ in, const float* __restrict__ xa, con
     const u64 wl[4] = {pk(w0.x, w1.x), pk(w0.y, w1.y), pk(w0.z, w1.z), pk(w0.w, w1.w)};   // (ch, ch+1) x input plane
     const u64 wh[4] = {pk(w2.x, w3.x), pk(w2.y, w3.y), pk(w2.z, w3.z), pk(w2.w, w3.w)};   // (ch+2, ch+3)
     const u64 bl = pk(bv.x, bv.y), bh = pk(bv.z, bv.w);
+    int r = 0, c = tg >> 3;                                // pixel (tg >> 3) + 16 k, advanced incrementally (no division)
 #pragma unroll 4
     for (int k = 0; k < 12; ++k) {
         const int px = (tg >> 3) + 16 * k;
         if (px >= 180) break;
-        const int r = px / 18, c = px - r * 18;
+        if (k > 0) { c += 16; if (c >= 18) { c -= 18; r += 1; } }
         const int Y = y0 - 1 + r, X = x0 - 1 + c;
         u64 lo = bl, hi = bh;
 #pragma unroll

@@ -62,6 +62,7 @@ constexpr uint32_t kABytes = kTileM * kKBlock * 2;   // 16 KB per hi or lo
 constexpr uint32_t kAStage = 2 * kABytes;            // hi + lo
 constexpr uint32_t kEpiWarpBuf = 32 * 32 * 4;        // 4 KB: 32 pixel rows x 32 fp32 of one epilogue warp
 constexpr uint32_t kSmemLimit = 232448;              // 227 KB
+constexpr int kRgbBias = 3 * 256, kRgbFir = 3 * 256 + 4;   // offsets inside the torgb table s_rgb
 constexpr uint32_t kStaticSmem = 4096;               // barriers + torgb table (static __shared__), rounded up
 
 struct Params {
@@ -276,7 +277,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
     //            [24,32) full_b  [32,40) empty_b  [40,42) full_acc  [42,44) empty_acc
     __shared__ __align__(8) uint64_t bars[44];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) float s_rgb[3 * 128 + 4 + 48];   // torgb weights [3][cout<=128], bias[3(+1)], fir[16][3]
+    __shared__ __align__(16) float s_rgb[3 * 256 + 4 + 48];   // torgb weights [3][cout<=256], bias[3(+1)], fir[16][3]
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -309,8 +310,8 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
     }
     if (p.torgb) {
         for (int i = threadIdx.x; i < 3 * p.cout; i += kThreads) s_rgb[i] = __ldg(p.rgb_w + i);
-        if (threadIdx.x < 3) s_rgb[3 * 128 + threadIdx.x] = __ldg(p.rgb_b + threadIdx.x);
-        if (threadIdx.x < 48 && p.img_lo) s_rgb[3 * 128 + 4 + threadIdx.x] = __ldg(p.rgb_fir + threadIdx.x);
+        if (threadIdx.x < 3) s_rgb[kRgbBias + threadIdx.x] = __ldg(p.rgb_b + threadIdx.x);
+        if (threadIdx.x < 48 && p.img_lo) s_rgb[kRgbFir + threadIdx.x] = __ldg(p.rgb_fir + threadIdx.x);
     }
     if (a_dw && p.off_dw != 0xFFFFFFFFu) {   // depthwise taps + bias for all channels: read per chunk by every prologue thread
         float* sdw = reinterpret_cast<float*>(smem_gen + p.off_dw);
@@ -470,6 +471,9 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
         const uint32_t stage_base = smem_base + p.off_epi + (uint32_t)(q * p.epi_bufs) * kEpiWarpBuf;
         for (int it = 0; it < my_tiles; ++it) {
             const TileCoord tc = decode_tile(p, blockIdx.x + it * gridDim.x);
+          // torgb partial sums live across the N halves of the tile (nts = 2: the same thread drains both regions of its pixel)
+          P2 rgb0 = p2zero(), rgb1 = p2zero(), rgb2 = p2zero();   // (even, odd) partial sums of the three torgb outputs
+          float lo_tap[12];
           for (int sub = 0; sub < nts; ++sub) {
             // accumulator region + the parity of its current use: consecutive tiles alternate regions (nts = 1), or
             // every tile uses both regions for its two N halves (nts = 2)
@@ -482,8 +486,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
             float nz = 0.f;
             const int pimg = tc.n0 + img_l, poy = tc.y0 + yl, pox = tc.x0 + xl;
             if (p.noise) nz = __ldg(p.noise + poy * p.W + pox);
-            float lo_tap[12];
-            if (p.torgb && p.img_lo) {
+            if (p.torgb && p.img_lo && sub == 0) {
                 const int h = p.H >> 1, w = p.W >> 1;
 #pragma unroll
                 for (int a = 0; a < 2; ++a)
@@ -499,7 +502,6 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
             mbar_wait(full_acc(e), use_parity, 300 + e, p.error_flag);
             tc_fence_after();
             const float scale_g = p.inv_scale * kActGain, nz_g = nz * kActGain;
-            P2 rgb0 = p2zero(), rgb1 = p2zero(), rgb2 = p2zero();   // (even, odd) partial sums of the three torgb outputs
             float* out_px = p.out + (((size_t)pimg * p.H + poy) * p.W + pox) * p.cout + chan0;
             for (int j = 0; j < chunks; ++j) {
                 uint32_t v[32];
@@ -543,9 +545,9 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                     }
                 }
                 if (p.torgb) {   // 1x1 conv Cout -> 3 on the activated row: even/odd partial sums, packed FMAs, weights broadcast from smem
-                    const float4* w0 = reinterpret_cast<const float4*>(s_rgb + j * 32);
-                    const float4* w1 = reinterpret_cast<const float4*>(s_rgb + p.cout + j * 32);
-                    const float4* w2 = reinterpret_cast<const float4*>(s_rgb + 2 * p.cout + j * 32);
+                    const float4* w0 = reinterpret_cast<const float4*>(s_rgb + chan0 + j * 32);
+                    const float4* w1 = reinterpret_cast<const float4*>(s_rgb + p.cout + chan0 + j * 32);
+                    const float4* w2 = reinterpret_cast<const float4*>(s_rgb + 2 * p.cout + chan0 + j * 32);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 a = w0[i], b = w1[i], c = w2[i];
@@ -581,11 +583,10 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                 }
                 buf = (buf + 1 == p.epi_bufs) ? 0 : buf + 1;
             }
-            if (p.torgb) {
+            if (p.torgb && sub == nts - 1) {
                 // img = upsample(img_lo) + (torgb(x) + b)   (migan_inference.py:308-313); planar NCHW
                 if (pimg < p.n) {
-                    float r[3] = {unpk(rgb0).x + unpk(rgb0).y + s_rgb[384], unpk(rgb1).x + unpk(rgb1).y + s_rgb[385],
-                                  unpk(rgb2).x + unpk(rgb2).y + s_rgb[386]};
+                    float r[3] = {rgb0.x + rgb0.y + s_rgb[kRgbBias], rgb1.x + rgb1.y + s_rgb[kRgbBias + 1], rgb2.x + rgb2.y + s_rgb[kRgbBias + 2]};
                     if (p.img_lo) {
                         float up[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -595,7 +596,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                                 const int ty = (poy & 1) + 2 * a, tx = (pox & 1) + 2 * bb;
 #pragma unroll
                                 for (int k = 0; k < 3; ++k)
-                                    up[k] = fmaf(s_rgb[388 + (ty * 4 + tx) * 3 + k], lo_tap[(a * 2 + bb) * 3 + k], up[k]);
+                                    up[k] = fmaf(s_rgb[kRgbFir + (ty * 4 + tx) * 3 + k], lo_tap[(a * 2 + bb) * 3 + k], up[k]);
                             }
 #pragma unroll
                         for (int k = 0; k < 3; ++k) r[k] = up[k] + r[k];
@@ -755,7 +756,7 @@ const char* sepconv_tc_plan_ex(SepconvTcArgs* args, const SepconvTcDesc& d) {
     p.n_tile = (cout == 64) ? 64 : 128;
     // Two 128-column accumulator regions can hold the two N halves of one M tile: the A operand (and for the fused
     // sources the whole prologue) is then produced once per pixel tile instead of once per N tile.
-    p.nt_share = (cout >= 256 && env_int("MIGAN_TC_NT_SHARE", 1) != 0) ? 2 : 1;
+    p.nt_share = (cout >= 256 && (env_int("MIGAN_TC_NT_SHARE", 1) != 0 || (d.rgb && cout == 256))) ? 2 : 1;   // fused torgb at 256 needs both halves in one CTA
     p.num_n_tiles = cout / (p.n_tile * p.nt_share);
     p.num_kb = cin / kKBlock;
     if (dw) {   // spatial tiles with halo
@@ -792,7 +793,7 @@ const char* sepconv_tc_plan_ex(SepconvTcArgs* args, const SepconvTcDesc& d) {
 
     p.store_out = 1;
     if (d.rgb) {
-        if (p.num_n_tiles != 1 || p.nt_share != 1 || cout > 128) return "fused torgb needs all output channels in one accumulator region (cout <= 128)";
+        if (p.num_n_tiles != 1 || cout > 256) return "fused torgb needs all output channels of a pixel tile in one CTA (cout <= 256)";
         p.torgb = 1; p.store_out = d.rgb->store_out;
         p.rgb_w = d.rgb->w; p.rgb_b = d.rgb->b; p.rgb_fir = d.rgb->fir; p.img_lo = d.rgb->img_lo; p.img_out = d.rgb->img_out;
     }
@@ -814,16 +815,20 @@ const char* sepconv_tc_plan_ex(SepconvTcArgs* args, const SepconvTcDesc& d) {
     {
         const int a_st = dw ? 2 : 3;
         const int b_res = p.b_resident ? p.num_kb : 0;
-        const int in_hi = dw ? 4 : 0, in_lo = dw ? 2 : 0;
+        // input ring depths to try, deepest first (even: each prologue group owns every other stage).  Round-2 ncu: with two
+        // stages per group the prologue warps of a 128 -> 128 layer wait for TMA data 29 % of the time.
+        const int max_in = env_int("MIGAN_TC_MAX_IN", 6);
+        std::vector<int> ins;
+        if (dw) { for (int v = 6; v >= 2; v -= 2) if (v <= max_in) ins.push_back(v); } else ins.push_back(0);
         const int bopts[2] = {b_res ? b_res : 3, b_res ? b_res : 2};
         for (int bi = 0; bi < 2; ++bi) {
             if (bi == 1 && bopts[1] == bopts[0]) break;
             const int bs = bopts[bi];
-            if (!p.store_out) { cands.push_back({in_hi, 0, 0, bs, a_st}); cands.push_back({in_lo, 0, 0, bs, a_st}); continue; }
-            if (epi_mode != 2) { cands.push_back({in_hi, 2, 0, bs, a_st}); cands.push_back({in_hi, 1, 0, bs, a_st}); }
-            if (epi_mode != 1) cands.push_back({in_hi, 0, 1, bs, a_st});
-            if (epi_mode != 2) { cands.push_back({in_lo, 2, 0, bs, a_st}); cands.push_back({in_lo, 1, 0, bs, a_st}); }
-            if (epi_mode != 1) cands.push_back({in_lo, 0, 1, bs, a_st});
+            for (int in_st : ins) {
+                if (!p.store_out) { cands.push_back({in_st, 0, 0, bs, a_st}); continue; }
+                if (epi_mode != 2) { cands.push_back({in_st, 2, 0, bs, a_st}); cands.push_back({in_st, 1, 0, bs, a_st}); }
+                if (epi_mode != 1) cands.push_back({in_st, 0, 1, bs, a_st});
+            }
         }
     }
     uint32_t smem_bytes = 0;
