@@ -351,6 +351,160 @@ cudaError_t launch_dw3x3_down(const float* in, const float* w9, const float* bia
 }
 
 // --------------------------------------------------------------------------------------
+// Tensor-core feed variant of the kernel above: same thread mapping and row walk, specialised for the pre-split fp16
+// hi/lo output.  Round-2 ncu of the generic kernel: 54 % issue utilisation, 23 % of the instructions were address
+// arithmetic (eight 64-bit column pointers, runtime C) and 13 % scalar min/max.  Here
+//   * C is a template parameter: one row pointer, every column / tap offset is an immediate;
+//   * the taps and bias arrive pre-multiplied by kActSplitScale * sqrt(2) (the table the tcgen05 prologue uses), so the
+//     activation is clamp(max(v, 0.2 v), +-256 * 64) -- one packed multiply, one 3-input max and one min per value -- and
+//     the FIR output is already scaled for the fp16 hi/lo split (the FIR is linear);
+//   * packed fp32x2 arithmetic goes through the sm_100 float2 intrinsics (no inline-asm register moves).
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ float fmax3f(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+
+template <int RS, int C>
+__global__ void __launch_bounds__(256, 2)
+dw3x3_down_split_kernel(const float* __restrict__ in, const float* __restrict__ w9s, const float* __restrict__ biass,
+                        const float* __restrict__ fir16, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                        uint32_t items, int lw2, int lh2, int lstrips) {
+    constexpr int CP = C / 2;                              // channel pairs
+    constexpr float kLim = kActClamp * kActSplitScale;
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    const int W2 = 1 << lw2, H2 = 1 << lh2, W = 2 * W2, H = 2 * H2;
+    const int c = (int)(idx % CP) * 2;
+    uint32_t t = idx / CP;
+    const int ox0 = (int)(t & ((W2 >> 1) - 1)) * 2;
+    t >>= (lw2 - 1);
+    const int strip = (int)(t & ((1u << lstrips) - 1));
+    const size_t img = t >> lstrips;
+    const int oy0 = strip * RS;
+
+    extern __shared__ float s_fir[];                       // [16][C]
+    for (int i = threadIdx.x; i < 16 * C; i += 256) s_fir[i] = __ldg(fir16 + i);
+    __syncthreads();
+    if (idx >= items) return;
+    const float2* firp = reinterpret_cast<const float2*>(s_fir + c);
+    float2 wv[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wv[k] = __ldg(reinterpret_cast<const float2*>(w9s + k * C + c));
+    const float2 bv = __ldg(reinterpret_cast<const float2*>(biass + c));
+
+    const int iy_first = 2 * oy0 - 2;
+    const bool left_ok = (ox0 > 0), right_ok = (ox0 + 2 < W2);            // columns 2ox0-2, 2ox0-1 / 2ox0+4, 2ox0+5 exist
+    // one row pointer: column j of the 8-column window is at j * C floats (immediate offsets)
+    const float* rowp = in + ((img * H + iy_first) * (size_t)W + (2 * ox0 - 2)) * C + c;
+    const size_t row_stride = (size_t)W * C;
+
+    float2 dw[3][6];
+#pragma unroll
+    for (int s2 = 0; s2 < 3; ++s2)
+#pragma unroll
+        for (int tx = 0; tx < 6; ++tx) dw[s2][tx] = bv;
+    const float2 zero2 = make_float2(0.f, 0.f), alpha2 = make_float2(kLreluAlpha, kLreluAlpha);
+    float2 accA[2] = {zero2, zero2}, accB[2] = {zero2, zero2};   // FIR accumulators of output rows k-1 / k, columns ox0 / ox0+1
+
+    float2 vn[8];
+    auto fetch_row = [&](int r) {
+        const int iy = iy_first + r;
+        const bool rowok = (iy >= 0 && iy < H);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool ok = rowok && (j >= 2 || left_ok) && (j < 6 || right_ok);
+            vn[j] = ok ? __ldg(reinterpret_cast<const float2*>(rowp + j * C)) : zero2;
+        }
+        rowp += row_stride;
+    };
+    fetch_row(0);
+#pragma unroll
+    for (int r = 0; r < 2 * RS + 4; ++r) {
+        const int iy = iy_first + r;
+        float2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = vn[j];
+        if (r + 1 < 2 * RS + 4) fetch_row(r + 1);
+        // ky = 2 -> depthwise row iy-1 (slot (r+1)%3, completes), ky = 1 -> row iy (slot (r+2)%3), ky = 0 -> row iy+1 (slot r%3)
+#pragma unroll
+        for (int tx = 0; tx < 6; ++tx) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                dw[(r + 1) % 3][tx] = __ffma2_rn(wv[6 + kx], v[tx + kx], dw[(r + 1) % 3][tx]);
+                dw[(r + 2) % 3][tx] = __ffma2_rn(wv[3 + kx], v[tx + kx], dw[(r + 2) % 3][tx]);
+                dw[r % 3][tx] = __ffma2_rn(wv[kx], v[tx + kx], dw[r % 3][tx]);
+            }
+        }
+        if (r >= 2) {                                     // depthwise row gy = iy - 1 is complete
+            const int q = r - 2;                          // gy = 2*oy0 - 1 + q
+            const int gy = iy - 1;
+            const int tyB = (q & 1) ? 1 : 0, tyA = tyB + 2;
+            if (gy >= 0 && gy < H) {
+#pragma unroll
+                for (int tx = 0; tx < 6; ++tx) {
+                    if ((tx == 0 && !left_ok) || (tx == 5 && !right_ok)) continue;   // depthwise column outside the image: zero
+                    const float2 a = dw[(r + 1) % 3][tx], b = __fmul2_rn(a, alpha2);
+                    const float2 d = make_float2(fminf(fmax3f(a.x, b.x, -kLim), kLim), fminf(fmax3f(a.y, b.y, -kLim), kLim));
+                    if (tx < 4) {                         // tap column tx of output ox0
+                        accB[0] = __ffma2_rn(firp[(tyB * 4 + tx) * CP], d, accB[0]);
+                        accA[0] = __ffma2_rn(firp[(tyA * 4 + tx) * CP], d, accA[0]);
+                    }
+                    if (tx >= 2) {                        // tap column tx-2 of output ox0+1
+                        accB[1] = __ffma2_rn(firp[(tyB * 4 + tx - 2) * CP], d, accB[1]);
+                        accA[1] = __ffma2_rn(firp[(tyA * 4 + tx - 2) * CP], d, accA[1]);
+                    }
+                }
+            }
+            if ((q & 1) && q >= 3) {                      // gy = 2k even: last tap of output row k-1 = oy0 + (q-3)/2
+                const int orow = oy0 + ((q - 3) >> 1);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const size_t o = ((img * H2 + orow) * W2 + ox0 + e) * (size_t)C + c;
+                    const float2 ov = accA[e];            // already * kActSplitScale
+                    const __half2 h = __floats2half2_rn(ov.x, ov.y);
+                    const float2 hf = __half22float2(h);
+                    *reinterpret_cast<__half2*>(out_hi + o) = h;
+                    *reinterpret_cast<__half2*>(out_lo + o) = __floats2half2_rn(ov.x - hf.x, ov.y - hf.y);
+                }
+            }
+            if (q & 1) { accA[0] = accB[0]; accA[1] = accB[1]; accB[0] = zero2; accB[1] = zero2; }
+        }
+#pragma unroll
+        for (int tx = 0; tx < 6; ++tx) dw[(r + 1) % 3][tx] = bv;   // slot is reused by depthwise row iy + 2
+    }
+}
+
+template <int RS, int C>
+static void launch_down_split_inst(const float* in, const float* w9s, const float* biass, const float* fir16, __half* hi, __half* lo,
+                                   uint32_t items, int W2, int H2, int strips, cudaStream_t s) {
+    dw3x3_down_split_kernel<RS, C><<<(items + 255) / 256, 256, 16 * C * sizeof(float), s>>>(in, w9s, biass, fir16, hi, lo, items,
+                                                                                           host_log2(W2), host_log2(H2), host_log2(strips));
+}
+
+// w9s / biass: depthwise taps and bias * kActSplitScale * sqrt(2).  C in {64, 128, 256, 512}.
+cudaError_t launch_dw3x3_down_split(const float* in, const float* w9s, const float* biass, const float* fir16,
+                                    __half* out_hi, __half* out_lo, int n, int H, int W, int C, cudaStream_t s) {
+    const int H2 = H / 2, W2 = W / 2;
+    if (W2 < 2 || (C != 64 && C != 128 && C != 256 && C != 512)) return cudaErrorInvalidValue;
+    const int rs = (H2 >= 8) ? 8 : 4, strips = H2 / rs;
+    if (strips < 1) return cudaErrorInvalidValue;
+    const size_t per_img = (size_t)strips * (W2 / 2) * (C / 2);
+    return for_image_groups(n, per_img, [&](int i0, int cnt) {
+        const uint32_t items = (uint32_t)(per_img * cnt);
+        const float* ip = in + (size_t)i0 * H * W * C;
+        __half* hp = out_hi + (size_t)i0 * H2 * W2 * C;
+        __half* lp = out_lo + (size_t)i0 * H2 * W2 * C;
+#define MIGAN_DOWN_CASE(RS_, C_) launch_down_split_inst<RS_, C_>(ip, w9s, biass, fir16, hp, lp, items, W2, H2, strips, s)
+        if (rs == 8) {
+            if (C == 64) MIGAN_DOWN_CASE(8, 64); else if (C == 128) MIGAN_DOWN_CASE(8, 128);
+            else if (C == 256) MIGAN_DOWN_CASE(8, 256); else MIGAN_DOWN_CASE(8, 512);
+        } else {
+            if (C == 64) MIGAN_DOWN_CASE(4, 64); else if (C == 128) MIGAN_DOWN_CASE(4, 128);
+            else if (C == 256) MIGAN_DOWN_CASE(4, 256); else MIGAN_DOWN_CASE(4, 512);
+        }
+#undef MIGAN_DOWN_CASE
+    });
+}
+
+
+// --------------------------------------------------------------------------------------
 // 2x FIR up-sampling (polyphase: only the taps that meet a non-zero of the zero-inserted
 // signal) + noise + act + skip.  out[o] = sum_t f[t] * z[o + t - 2], z[2i] = x[i], z[odd] = 0.
 // --------------------------------------------------------------------------------------

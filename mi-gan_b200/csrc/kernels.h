@@ -26,6 +26,10 @@ cudaError_t launch_dw3x3(const float* in, const float* w9, const float* bias, fl
 cudaError_t launch_dw3x3_down(const float* in, const float* w9, const float* bias, const float* fir16,
                               float* out_f32, __half* out_hi, __half* out_lo,
                               int n, int H, int W, int C, cudaStream_t s);
+// Same stage specialised for the tensor-core feed (pre-split fp16 hi/lo output only): w9s / biass are the taps and bias
+// pre-multiplied by kActSplitScale * sqrt(2); C in {64, 128, 256, 512}.
+cudaError_t launch_dw3x3_down_split(const float* in, const float* w9s, const float* biass, const float* fir16,
+                                    __half* out_hi, __half* out_lo, int n, int H, int W, int C, cudaStream_t s);
 // 2x polyphase FIR up-sampling of the raw 1x1-conv output + noise + lrelu_agc + skip add.
 // t [n,h,w,C] -> out [n,2h,2w,C]; fir16 [16][C] (gain included); noise [2h*2w] (already
 // multiplied by noise_strength) or null; skip [n,2h,2w,C] or null (added AFTER the activation).
