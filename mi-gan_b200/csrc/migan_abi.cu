@@ -582,9 +582,12 @@ struct PlanBuilder {
         s.tap = name; s.tap_src = src; s.tapC = C; s.tapH = H; s.tapW = W; s.tap_planar = planar; s.tap_flags = flags;
     }
 
-    static int fuse_mask() {            // MIGAN_FUSE bit 0: UP, bit 1: STEM (debug / A-B measurements; default all on)
+    static int fuse_mask_dw() {         // MIGAN_FUSE bit 2: run the depthwise stage of the small Cout = 512 levels (res <= 32) inside the
+        return fuse_mask() & 4;         // tensor-core kernel (its prologue repeats per N tile, which is cheap there) instead of as its own launch
+    }
+    static int fuse_mask() {            // MIGAN_FUSE bit 0: UP, bit 1: STEM, bit 2: small-level depthwise (debug / A-B measurements; default all on)
         const char* e = getenv("MIGAN_FUSE");
-        return e ? atoi(e) : 3;
+        return e ? atoi(e) : 7;
     }
 
     // Emit one SeparableConv2d reading `in` (NHWC [n,res_in,res_in,cin]); `skip` is added after the
@@ -614,7 +617,7 @@ struct PlanBuilder {
             set_tap(s, L.p + "dw_act", S[t1], L.cin, L.res_in, L.res_in);
             steps.push_back(s);
             gemm_in = S[t1];
-        } else if (L.cout >= 512 && !rgb) {
+        } else if (L.cout >= 512 && !rgb && (L.res_in >= 64 || fuse_mask_dw() == 0)) {
             // Cout spans 4 accumulator regions: a fused prologue would re-run the depthwise stage, so run it once as its
             // own kernel and hand the GEMM a pre-split operand (these layers are small: res <= 64)
             Step s; s.kind = K_DW; s.L = &L; s.in = in; s.n = n; s.H = L.res_in; s.W = L.res_in; s.C = L.cin;

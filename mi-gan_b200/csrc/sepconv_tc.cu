@@ -757,7 +757,6 @@ const char* sepconv_tc_plan_ex(SepconvTcArgs* args, const SepconvTcDesc& d) {
     // Two 128-column accumulator regions can hold the two N halves of one M tile: the A operand (and for the fused
     // sources the whole prologue) is then produced once per pixel tile instead of once per N tile.
     p.nt_share = (cout >= 256 && (env_int("MIGAN_TC_NT_SHARE", 1) != 0 || (d.rgb && cout == 256))) ? 2 : 1;   // fused torgb at 256 needs both halves in one CTA
-    p.num_n_tiles = cout / (p.n_tile * p.nt_share);
     p.num_kb = cin / kKBlock;
     if (dw) {   // spatial tiles with halo
         p.tile_w = res >= 16 ? 16 : res;
@@ -768,6 +767,16 @@ const char* sepconv_tc_plan_ex(SepconvTcArgs* args, const SepconvTcDesc& d) {
     }
     p.tile_n = kTileM / (p.tile_w * p.tile_h);
     p.tiles_x = res / p.tile_w; p.tiles_y = res / p.tile_h; p.tiles_n = (n + p.tile_n - 1) / p.tile_n;
+    int dev0 = 0, sms0 = 148;
+    cudaGetDevice(&dev0);
+    cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+    // Few pixel tiles (the 4 x 4 ... 16 x 16 levels at small batches): a CTA that owns 256 output channels streams the whole
+    // weight matrix and issues every MMA of its tile while most SMs idle.  Narrow N tiles spread the layer over 4 x the CTAs.
+    if (!d.rgb && cout >= 256 && p.tiles_x * p.tiles_y * p.tiles_n * (cout / (p.n_tile * p.nt_share)) * 2 < sms0 &&
+        env_int("MIGAN_TC_SMALL_N", 1) != 0) {
+        p.n_tile = 64; p.nt_share = 1;
+    }
+    p.num_n_tiles = cout / (p.n_tile * p.nt_share);
     p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.num_n_tiles;
     auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
     p.l_tx = ilog2(p.tiles_x); p.l_ty = ilog2(p.tiles_y); p.l_nt = ilog2(p.num_n_tiles);
