@@ -246,3 +246,43 @@ def test_full_size_batch_properties(cuda_device, path):
     assert mx < TOL_MAX_ABS and mean < TOL_MEAN_ABS
     y2 = g(x[16:].contiguous().to(cuda_device))              # same images, different batch slot
     assert torch.equal(y[16:], y2)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("R", [8, 16, 32])
+def test_small_resolutions(cuda_device, path, R):
+    """R = 8 / 16 / 32 are valid constructor arguments (migan_inference.py:214-223): every level has 512 channels, the stem
+    is 4 -> 512 and the top torgb runs un-fused.  Final output and every intermediate against the oracle."""
+    N = 3
+    g, sd = make_model(R, path)
+    x = O.make_input(R, N, seed=13)
+    taps = {}
+    want = O.generator_forward(sd, x, R, taps=taps)
+    xd = x.to(cuda_device)
+    mx, mean = errs(g(xd), want)
+    print("R=%d path=%s max-abs=%.3e mean-abs=%.3e" % (R, path, mx, mean))
+    assert mx < TOL_MAX_ABS and mean < TOL_MEAN_ABS
+    bad = []
+    for name, shape in g.tap_names():
+        _, got = g.forward_with_tap(xd, name, shape)
+        w = taps[name[: -len("_skip")]] + taps["feat%d" % shape[1]] if name.endswith("out_skip") else taps[name]
+        e, _ = errs(got, w)
+        if not (e < 2e-4 * max(float(w.abs().max()), 1.0)):
+            bad.append((name, e))
+    assert not bad, "first mismatching stages: %s" % bad[:5]
+
+
+def test_migan256_batch32(cuda_device):
+    """BASELINE.json configs[1] size (migan-256, 32 images, tensor-core path): oracle on a 3-image sample, finite everywhere,
+    and image-by-image agreement with a different batch composition."""
+    R, N = 256, 32
+    g, sd = make_model(R, "tc")
+    x = O.make_input(R, N, seed=91)
+    y = g(x.to(cuda_device))
+    assert torch.isfinite(y).all()
+    pick = [0, 17, 31]
+    mx, mean = errs(y[pick], O.generator_forward(sd, x[pick], R))
+    print("256/32 tc max-abs=%.3e mean-abs=%.3e" % (mx, mean))
+    assert mx < TOL_MAX_ABS and mean < TOL_MEAN_ABS
+    y2 = g(x[8:24].contiguous().to(cuda_device))
+    assert torch.equal(y[8:24], y2)

@@ -1,5 +1,4 @@
-"""Staged (default-off) code paths that have NOT yet run on hardware.  Skipped unless MIGAN_RUN_STAGED=1, so that a
-first-run failure (a trap in a tcgen05 kernel poisons the CUDA context) cannot take the validated suites down with it.
+"""Opt-in code paths (off by default) -- validated on a B200 in round 2 (profiles/r02_comodgan_tc_route.log).
 
   COMOD_GEMM=tc   Co-Mod-GAN plain / strided / 1x1 convolutions on the tcgen05 GEMM of the MI-GAN path (sepconv_tc.cu in its
                   A_TMA configuration, K up to 4608) fed by an fp16 hi/lo split im2col.  Operand packing is covered on the
@@ -14,8 +13,7 @@ import torch
 from oracle import comodgan_oracle as C
 from oracle import migan_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MIGAN_RUN_STAGED") != "1", reason="staged path: set MIGAN_RUN_STAGED=1")]
+pytestmark = [pytest.mark.gpu]
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
