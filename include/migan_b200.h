@@ -72,6 +72,15 @@ size_t migan_workspace_bytes(const migan_ctx* ctx, int n);
 int migan_forward(migan_ctx* ctx, const float* x, float* y, int n,
                   void* workspace, size_t workspace_bytes, int path, void* stream);
 
+/* Latency form for small batches (the reference's primary caller runs batch 1: scripts/demo.py:125-142): the launch
+ * sequence of one forward is captured ONCE into a CUDA graph that works on fixed staging buffers at the end of the
+ * workspace, and replayed per call between two device-to-device copies (x in, y out) -- 3 submissions instead of ~50.
+ * Same contract as migan_forward (DEVICE x / y, asynchronous on `stream`); the graph is rebuilt when n, path, the
+ * workspace or the weights change.  workspace_bytes must be >= migan_workspace_bytes(n) + migan_graph_staging_bytes(n). */
+size_t migan_graph_staging_bytes(const migan_ctx* ctx, int n);
+int migan_forward_graph(migan_ctx* ctx, const float* x, float* y, int n,
+                        void* workspace, size_t workspace_bytes, int path, void* stream);
+
 /* Same with HOST x / y (pinned for full speed): H2D copy, forward, D2H copy; y_host is complete on return.
  * The batch is split into two micro-batches whose copies overlap the kernels (three streams).  The device
  * staging buffers (two slots) live at the end of the workspace:

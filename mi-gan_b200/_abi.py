@@ -24,6 +24,8 @@ SYMBOLS = [
     ("migan_finalize_weights", c_int, [c_void_p]),
     ("migan_workspace_bytes", c_size_t, [c_void_p, c_int]),
     ("migan_forward", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    ("migan_graph_staging_bytes", c_size_t, [c_void_p, c_int]),
+    ("migan_forward_graph", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     ("migan_host_staging_bytes", c_size_t, [c_void_p, c_int]),
     ("migan_forward_host", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     ("migan_forward_host_async", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),

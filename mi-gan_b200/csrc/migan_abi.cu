@@ -170,6 +170,11 @@ struct migan_ctx {
     bool slot_used[2] = {false, false};
     const void* slot_base[2] = {nullptr, nullptr};   // staging memory each slot last used (re-ordered after the caller's stream when it changes)
     unsigned host_calls = 0;
+    // captured forward (migan_forward_graph): valid for one (n, path, workspace)
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaStream_t s_cap = nullptr;
+    int graph_n = 0, graph_path = -1, graph_launches = 0;
+    void* graph_ws = nullptr;
     int tap_cache_path = -1;          // tap enumeration cache (migan_tap_info)
     std::vector<std::pair<std::string, std::array<int, 3>>> tap_cache;
 };
@@ -319,6 +324,8 @@ int migan_destroy(migan_ctx* ctx) {
         if (ctx->slot_compute_done[i]) cudaEventDestroy(ctx->slot_compute_done[i]);
         if (ctx->slot_out_done[i]) cudaEventDestroy(ctx->slot_out_done[i]);
     }
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->s_cap) cudaStreamDestroy(ctx->s_cap);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->arena && ctx->device >= 0) {
@@ -522,6 +529,7 @@ int migan_finalize_weights(migan_ctx* ctx) {
     CUDA_TRY(cudaMemcpy(ctx->arena, ab.bytes.data(), ab.bytes.size(), cudaMemcpyHostToDevice));
     for (auto& f : fix) *f.first = static_cast<unsigned char*>(ctx->arena) + f.second;
     ctx->plan = Plan();  // pointers changed
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
     ctx->finalized = true;
     return MIGAN_OK;
 }
@@ -908,6 +916,56 @@ int migan_forward(migan_ctx* ctx, const float* x, float* y, int n, void* workspa
         if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->events[2 * i + 1], st));
         ++i;
     }
+    return MIGAN_OK;
+}
+
+size_t migan_graph_staging_bytes(const migan_ctx* ctx, int n) {
+    if (!ctx || n <= 0) return 0;
+    const size_t px = (size_t)n * ctx->resolution * ctx->resolution * sizeof(float);
+    return align_up(4 * px, 1024) + align_up(3 * px, 1024);
+}
+
+int migan_forward_graph(migan_ctx* ctx, const float* x, float* y, int n, void* workspace, size_t workspace_bytes,
+                        int path, void* stream) {
+    if (!ctx || !x || !y || !workspace) return fail(MIGAN_ERR_INVALID, "null argument");
+    if (n <= 0) return fail(MIGAN_ERR_INVALID, "batch size must be positive, got %d", n);
+    const size_t ws = migan_workspace_bytes(ctx, n);
+    if (workspace_bytes < ws + migan_graph_staging_bytes(ctx, n))
+        return fail(MIGAN_ERR_WORKSPACE, "workspace too small for the graph staging buffers: %zu < %zu bytes", workspace_bytes,
+                    ws + migan_graph_staging_bytes(ctx, n));
+    const size_t px = (size_t)n * ctx->resolution * ctx->resolution * sizeof(float);
+    float* xg = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + ws);
+    float* yg = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + ws + align_up(4 * px, 1024));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!ctx->graph_exec || ctx->graph_n != n || ctx->graph_path != path || ctx->graph_ws != workspace || ctx->profiling || ctx->tap_dst) {
+        if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+        if (ctx->profiling || ctx->tap_dst) {   // per-launch events / taps need the plain launch sequence
+            CUDA_TRY(cudaMemcpyAsync(xg, x, 4 * px, cudaMemcpyDeviceToDevice, st));
+            if (int rc = migan_forward(ctx, xg, yg, n, workspace, ws, path, stream)) return rc;
+            CUDA_TRY(cudaMemcpyAsync(y, yg, 3 * px, cudaMemcpyDeviceToDevice, st));
+            return MIGAN_OK;
+        }
+        // one plain run first: validates the arguments, builds the plan and binds the stem's tensor map to xg outside the capture
+        CUDA_TRY(cudaMemcpyAsync(xg, x, 4 * px, cudaMemcpyDeviceToDevice, st));
+        if (int rc = migan_forward(ctx, xg, yg, n, workspace, ws, path, stream)) return rc;
+        // capture on a private stream: the caller's stream may be the legacy default stream, which cannot be captured
+        if (!ctx->s_cap) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_cap, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamBeginCapture(ctx->s_cap, cudaStreamCaptureModeThreadLocal));
+        const int rc = migan_forward(ctx, xg, yg, n, workspace, ws, path, ctx->s_cap);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(ctx->s_cap, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail(MIGAN_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(ce)); }
+        const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { ctx->graph_exec = nullptr; return fail(MIGAN_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+        ctx->graph_n = n; ctx->graph_path = path; ctx->graph_ws = workspace; ctx->graph_launches = ctx->last_launches;
+    }
+    CUDA_TRY(cudaMemcpyAsync(xg, x, 4 * px, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaGraphLaunch(ctx->graph_exec, st));
+    CUDA_TRY(cudaMemcpyAsync(y, yg, 3 * px, cudaMemcpyDeviceToDevice, st));
+    ctx->last_launches = ctx->graph_launches;
     return MIGAN_OK;
 }
 

@@ -91,12 +91,16 @@ class _Engine:
         _abi.check(self.lib.migan_finalize_weights(self.handle))
         self.weights_version = version
 
-    def workspace(self, n: int, host_staging: bool = False):
+    def workspace(self, n: int, host_staging=False):
+        """host_staging: False (device forward), True (host-buffer call: two staging slots) or "graph" (captured forward:
+        one staging slot)."""
         key = (n, host_staging)
         ws = self.workspaces.get(key)
         if ws is None:
             nbytes = self.lib.migan_workspace_bytes(self.handle, n)
-            if host_staging:
+            if host_staging == "graph":
+                nbytes += self.lib.migan_graph_staging_bytes(self.handle, n)
+            elif host_staging:
                 nbytes += self.lib.migan_host_staging_bytes(self.handle, n)
             raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
             off = (-raw.data_ptr()) % 1024
@@ -117,6 +121,8 @@ class Generator(nn.Module):
         arch.log2_resolution(resolution)  # ValueError for non powers of two (reference :214-216)
         self.resolution = resolution
         self.path = path  # None -> $MIGAN_B200_PATH -> "tc"
+        # batches up to this size go through the CUDA-graph replay of the forward (0 disables it)
+        self.graph_max_batch = int(os.environ.get("MIGAN_GRAPH_MAX_N", "4"))
         for key, shape, kind in arch.state_entries(resolution):
             *mods, leaf = key.split(".")
             node = self
@@ -207,10 +213,16 @@ class Generator(nn.Module):
         with torch.cuda.device(x.device):
             eng = self._engine(x.device)
             y = torch.empty((n, 3, self.resolution, self.resolution), dtype=torch.float32, device=x.device)
-            ws = eng.workspace(n)
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            _abi.check(eng.lib.migan_forward(eng.handle, x.data_ptr(), y.data_ptr(), n, ws.data_ptr(), ws.numel(),
-                                             self._path_id(), stream))
+            if n <= self.graph_max_batch:
+                # small batches (the demo runs batch 1) are launch-bound: replay the captured launch sequence
+                ws = eng.workspace(n, "graph")
+                _abi.check(eng.lib.migan_forward_graph(eng.handle, x.data_ptr(), y.data_ptr(), n, ws.data_ptr(), ws.numel(),
+                                                       self._path_id(), stream))
+            else:
+                ws = eng.workspace(n)
+                _abi.check(eng.lib.migan_forward(eng.handle, x.data_ptr(), y.data_ptr(), n, ws.data_ptr(), ws.numel(),
+                                                 self._path_id(), stream))
         return y
 
     @torch.no_grad()

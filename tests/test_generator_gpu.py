@@ -286,3 +286,25 @@ def test_migan256_batch32(cuda_device):
     assert mx < TOL_MAX_ABS and mean < TOL_MEAN_ABS
     y2 = g(x[8:24].contiguous().to(cuda_device))
     assert torch.equal(y[8:24], y2)
+
+
+def test_graph_replay_small_batches(cuda_device):
+    """Batches <= graph_max_batch replay a captured CUDA graph of the forward (the demo's batch-1 latency path): same kernels,
+    so bit-identical to the plain launch sequence; the graph follows weight reloads and batch-size changes."""
+    R = 128
+    g, sd = make_model(R, "tc")
+    xs = [O.make_input(R, n, seed=60 + n).to(cuda_device) for n in (1, 2, 1, 3)]
+    g.graph_max_batch = 0
+    plain = [g(x) for x in xs]
+    g.graph_max_batch = 4
+    for _ in range(2):                                     # second round replays existing graphs / re-captures on a size change
+        for x, want in zip(xs, plain):
+            assert torch.equal(g(x), want)
+    assert errs(plain[0], O.generator_forward(sd, xs[0].cpu(), R))[0] < TOL_MAX_ABS
+    sd2 = O.make_state_dict(R, seed=5)
+    g.load_state_dict(sd2)
+    y = g(xs[1])                                           # new weights: the old graph must not be replayed
+    assert errs(y, O.generator_forward(sd2, xs[1].cpu(), R))[0] < TOL_MAX_ABS
+    name, shape = g.tap_names()[3]
+    y_t, _ = g.forward_with_tap(xs[1], name, shape)        # taps fall back to the plain sequence
+    assert torch.equal(y_t, y)
