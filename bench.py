@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true",
                     help="N > 1: skip the output all-gather (shows what the collective costs; not the north_star configuration)")
+    ap.add_argument("--gather", default="ce", choices=["ce", "nccl"],
+                    help="N > 1: output all-gather by copy-engine peer reads + an 8-byte NCCL ready signal (default), or NCCL all_gather_into_tensor")
+    ap.add_argument("--masks", default="free_form", choices=["free_form", "blocks"], help="synthetic hole masks")
     ap.add_argument("--profile-out", default=None, help="write the per-launch table (JSON) here")
     args = ap.parse_args()
     if args.res is None:
@@ -214,7 +217,7 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        parallel.configure_overlap()                                # few NCCL channels + SMs left free for them
+        parallel.configure_overlap(gather=args.gather)              # nccl: few channels + SMs left free for them; ce: nothing reserved
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -225,9 +228,9 @@ def run_b200(args):
     model = migan_b200.Generator(R, path=args.path)
     model.load_state_dict(synthetic.export_style_state_dict(R, seed=1))
     model = model.to(dev).eval()
-    x_host = synthetic.synthetic_input(R, B, seed=1234 + rank).pin_memory()
+    x_host = synthetic.synthetic_input(R, B, seed=1234 + rank, masks=args.masks).pin_memory()
     x = x_host.to(dev)
-    sharded = parallel.ShardedGenerator(model) if (world > 1 and not args.no_gather) else None
+    sharded = parallel.ShardedGenerator(model, gather=args.gather) if (world > 1 and not args.no_gather) else None
     if sharded is not None:
         sharded.check_replicas(model.state_dict())
 
@@ -274,13 +277,23 @@ def run_b200(args):
 
     # ---- end-to-end through the host-buffer C-ABI call (pinned H2D + forward + D2H, every step) ----
     y_host = torch.empty((B, 3, R, R), dtype=torch.float32).pin_memory()
-    for _ in range(2):
-        model.forward_host(x_host, out=y_host)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        model.forward_host(x_host, out=y_host, wait=False)   # serving loop: batches submitted back to back ...
-    model.host_wait()                                         # ... every y has landed in host memory here
+    if sharded is None:
+        for _ in range(2):
+            model.forward_host(x_host, out=y_host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            model.forward_host(x_host, out=y_host, wait=False)   # serving loop: batches submitted back to back ...
+        model.host_wait()                                         # ... every y has landed in host memory here
+    else:   # N > 1: through ShardedGenerator -- host shard in, forward, all-gather, this rank's rows of the gathered tensor out
+        for _ in range(2):
+            sharded.forward_host_async(x_host, y_host)
+        sharded.host_wait()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            sharded.forward_host_async(x_host, y_host)
+        sharded.host_wait()
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -310,6 +323,8 @@ def run_b200(args):
         except Exception as exc:  # the uint8 path is an extra; the contract's e2e above does not depend on it
             e2e_u8 = {"error": str(exc)[:200]}
 
+    if sharded is not None:
+        sharded.close()
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -382,15 +397,18 @@ def run_b200(args):
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.path != "tc_fast" else "f16",
         "data": "synthetic",
-        "config": {"workload": "migan-%d Generator.forward, %d images/GPU%s" % (R, B, ", NCCL all-gather of outputs" if sharded is not None else (", no gather" if world > 1 else "")),
+        "config": {"workload": "migan-%d Generator.forward, %d images/GPU%s" % (R, B, (", all-gather of outputs (%s)" % ("copy-engine peer reads over NVLink + 8-byte NCCL ready signal" if args.gather == "ce" else "NCCL all_gather_into_tensor")) if sharded is not None else (", no gather" if world > 1 else "")),
+                   "masks": "free-form (rectangles + brush strokes, evaluate_fid_lpips.py protocol)" if args.masks == "free_form" else "8x8-cell blocks",
                    "path": args.path, "arithmetic": "fp32 CUDA-core depthwise/FIR; 1x1 convs on tcgen05 as fp16 hi/lo 3-pass split with fp32 accumulate"
                    if args.path == "tc" else args.path,
                    "global_batch": world * B, "weights": "seeded export-style random (unit-L2 filters)",
                    "l2": "per-step working set (input 134 MB + ~10 GB of activations at 512/32) exceeds the 126 MB L2; no flush needed",
                    "kernel_timing": "separate pass of K steps with cudaEvents around every launch",
-                   "e2e": "K host batches submitted back to back through migan_forward_host_async (pinned H2D + forward + D2H "
-                          "per batch, two staging slots so the copies of batch t+1 / t-1 run under the kernels of batch t), timed until the last "
-                          "output landed in host memory"},
+                   "e2e": ("K host batches submitted back to back through migan_forward_host_async (pinned H2D + forward + D2H "
+                           "per batch, two staging slots so the copies of batch t+1 / t-1 run under the kernels of batch t), timed until the last "
+                           "output landed in host memory") if sharded is None else
+                          ("K host shards per rank through ShardedGenerator.forward_host_async: pinned H2D, forward, all-gather, D2H of the "
+                           "rank's rows of the gathered tensor; copies of batch t+1 / t-1 run under the kernels of batch t")},
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8,
         "gpu_launches": launches_per_step * K,
     }
