@@ -98,10 +98,15 @@ int migan_host_wait(migan_ctx* ctx);
 /* uint8 request path (the callers' pre/post-processing fused around the forward, scripts/demo.py:56-66 and :135-142):
  * img_host u8 [n,R,R,3] (RGB, HWC), mask_host u8 [n,R,R] (255 = known pixel, anything else = hole) ->
  * out_host u8 [n,R,R,3] = known pixels of img, generated pixels elsewhere.  7 bytes per pixel cross PCIe instead of 28.
- * workspace_bytes must be >= migan_workspace_bytes(n) + migan_u8_staging_bytes(n).  Synchronous (out_host complete). */
+ * workspace_bytes must be >= migan_workspace_bytes(n) + migan_u8_staging_bytes(n) (two staging slots).
+ * migan_forward_u8 is synchronous (out_host complete on return); migan_forward_u8_async only enqueues -- consecutive calls
+ * alternate between the slots so that the copies of request t+1 / t-1 run under the kernels of request t, and
+ * migan_host_wait() blocks until every enqueued request has landed (buffers must stay valid and unmodified until then). */
 size_t migan_u8_staging_bytes(const migan_ctx* ctx, int n);
 int migan_forward_u8(migan_ctx* ctx, const uint8_t* img_host, const uint8_t* mask_host, uint8_t* out_host, int n,
                      void* workspace, size_t workspace_bytes, int path, void* stream);
+int migan_forward_u8_async(migan_ctx* ctx, const uint8_t* img_host, const uint8_t* mask_host, uint8_t* out_host, int n,
+                           void* workspace, size_t workspace_bytes, int path, void* stream);
 /* The two kernels on their own (DEVICE pointers): x[n,4,r,r] = cat([mask-0.5, img*mask]) and the composite of y[n,3,r,r]. */
 int b200_preprocess_u8(const uint8_t* img_hwc, const uint8_t* mask_hw, float* x_nchw, int n, int r, void* stream);
 int b200_postprocess_u8(const float* y_nchw, const uint8_t* img_hwc, const uint8_t* mask_hw, uint8_t* out_hwc, int n, int r,

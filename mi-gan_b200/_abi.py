@@ -32,6 +32,7 @@ SYMBOLS = [
     ("migan_host_wait", c_int, [c_void_p]),
     ("migan_u8_staging_bytes", c_size_t, [c_void_p, c_int]),
     ("migan_forward_u8", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    ("migan_forward_u8_async", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     ("b200_preprocess_u8", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     ("b200_postprocess_u8", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     ("migan_last_launch_count", c_int, [c_void_p]),

@@ -170,6 +170,11 @@ struct migan_ctx {
     bool slot_used[2] = {false, false};
     const void* slot_base[2] = {nullptr, nullptr};   // staging memory each slot last used (re-ordered after the caller's stream when it changes)
     unsigned host_calls = 0;
+    // uint8 request pipeline (migan_forward_u8 / _async): its own two staging slots and events
+    cudaEvent_t u8_in[2] = {nullptr, nullptr}, u8_compute_done[2] = {nullptr, nullptr}, u8_out_done[2] = {nullptr, nullptr}, u8_start = nullptr;
+    bool u8_used[2] = {false, false};
+    const void* u8_base[2] = {nullptr, nullptr};
+    unsigned u8_calls = 0;
     // captured forward (migan_forward_graph): valid for one (n, path, workspace)
     cudaGraphExec_t graph_exec = nullptr;
     cudaStream_t s_cap = nullptr;
@@ -324,6 +329,12 @@ int migan_destroy(migan_ctx* ctx) {
         if (ctx->slot_compute_done[i]) cudaEventDestroy(ctx->slot_compute_done[i]);
         if (ctx->slot_out_done[i]) cudaEventDestroy(ctx->slot_out_done[i]);
     }
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->u8_in[i]) cudaEventDestroy(ctx->u8_in[i]);
+        if (ctx->u8_compute_done[i]) cudaEventDestroy(ctx->u8_compute_done[i]);
+        if (ctx->u8_out_done[i]) cudaEventDestroy(ctx->u8_out_done[i]);
+    }
+    if (ctx->u8_start) cudaEventDestroy(ctx->u8_start);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     if (ctx->s_cap) cudaStreamDestroy(ctx->s_cap);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -1093,14 +1104,20 @@ int migan_forward_host_async(migan_ctx* ctx, const float* x_host, float* y_host,
     return forward_host_enqueue(ctx, x_host, y_host, n, workspace, workspace_bytes, path, stream, nullptr);
 }
 
-size_t migan_u8_staging_bytes(const migan_ctx* ctx, int n) {
-    if (!ctx || n <= 0) return 0;
+static size_t u8_slot_bytes(const migan_ctx* ctx, int n) {
     const size_t px = (size_t)n * ctx->resolution * ctx->resolution;
     return align_up(4 * px * sizeof(float), 1024) + align_up(3 * px * sizeof(float), 1024) + 2 * align_up(3 * px, 1024) + align_up(px, 1024);
 }
 
-int migan_forward_u8(migan_ctx* ctx, const uint8_t* img_host, const uint8_t* mask_host, uint8_t* out_host, int n,
-                     void* workspace, size_t workspace_bytes, int path, void* stream) {
+size_t migan_u8_staging_bytes(const migan_ctx* ctx, int n) {
+    if (!ctx || n <= 0) return 0;
+    return 2 * u8_slot_bytes(ctx, n);     // two slots: consecutive calls overlap
+}
+
+// Enqueue H2D(img, mask) -> preprocess -> forward -> postprocess -> D2H(out) for one uint8 request batch.  Same three-stream,
+// two-slot scheme as the fp32 host call: the copies of call c+1 / c-1 run under the kernels of call c.
+static int forward_u8_enqueue(migan_ctx* ctx, const uint8_t* img_host, const uint8_t* mask_host, uint8_t* out_host, int n,
+                              void* workspace, size_t workspace_bytes, int path, void* stream, int* slot_out) {
     if (!ctx || !img_host || !mask_host || !out_host || !workspace) return fail(MIGAN_ERR_INVALID, "null argument");
     if (n <= 0) return fail(MIGAN_ERR_INVALID, "batch size must be positive, got %d", n);
     const size_t ws = migan_workspace_bytes(ctx, n);
@@ -1109,7 +1126,9 @@ int migan_forward_u8(migan_ctx* ctx, const uint8_t* img_host, const uint8_t* mas
                     ws + migan_u8_staging_bytes(ctx, n));
     const int R = ctx->resolution;
     const size_t px = (size_t)n * R * R;
-    unsigned char* b = static_cast<unsigned char*>(workspace) + ws;
+    const int slot = (int)(ctx->u8_calls++ & 1);
+    unsigned char* sbase = static_cast<unsigned char*>(workspace) + ws + slot * u8_slot_bytes(ctx, n);
+    unsigned char* b = sbase;
     float* xd = reinterpret_cast<float*>(b);               b += align_up(4 * px * sizeof(float), 1024);
     float* yd = reinterpret_cast<float*>(b);               b += align_up(3 * px * sizeof(float), 1024);
     uint8_t* img_d = b;                                     b += align_up(3 * px, 1024);
@@ -1117,15 +1136,60 @@ int migan_forward_u8(migan_ctx* ctx, const uint8_t* img_host, const uint8_t* mas
     uint8_t* mask_d = b;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaSetDevice(ctx->device));
-    CUDA_TRY(cudaMemcpyAsync(img_d, img_host, 3 * px, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(mask_d, mask_host, px, cudaMemcpyHostToDevice, st));
+    if (!ctx->s_in) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot_compute_done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot_out_done[i], cudaEventDisableTiming));
+        }
+    }
+    if (!ctx->u8_start) {
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->u8_start, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->u8_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->u8_compute_done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->u8_out_done[i], cudaEventDisableTiming));
+        }
+    }
+    if (!ctx->u8_used[slot] || ctx->u8_base[slot] != sbase) {   // new staging memory: order the copy streams after the caller's stream once
+        CUDA_TRY(cudaEventRecord(ctx->u8_start, st));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->u8_start, 0));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->u8_start, 0));
+        ctx->u8_base[slot] = sbase;
+    }
+    if (ctx->u8_used[slot]) {
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->u8_compute_done[slot], 0));   // img_d / mask_d of this slot are free again
+        CUDA_TRY(cudaStreamWaitEvent(st, ctx->u8_out_done[slot], 0));              // out_d of this slot has been copied out
+    }
+    CUDA_TRY(cudaMemcpyAsync(img_d, img_host, 3 * px, cudaMemcpyHostToDevice, ctx->s_in));
+    CUDA_TRY(cudaMemcpyAsync(mask_d, mask_host, px, cudaMemcpyHostToDevice, ctx->s_in));
+    CUDA_TRY(cudaEventRecord(ctx->u8_in[slot], ctx->s_in));
+    CUDA_TRY(cudaStreamWaitEvent(st, ctx->u8_in[slot], 0));
     CUDA_TRY((cudaError_t)migan::launch_preprocess_u8(img_d, mask_d, xd, n, R, st));
     if (int rc = migan_forward(ctx, xd, yd, n, workspace, ws, path, stream)) return rc;
     CUDA_TRY((cudaError_t)migan::launch_postprocess_u8(yd, img_d, mask_d, out_d, n, R, st));
     ctx->last_launches += 2;
-    CUDA_TRY(cudaMemcpyAsync(out_host, out_d, 3 * px, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventRecord(ctx->u8_compute_done[slot], st));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->u8_compute_done[slot], 0));
+    CUDA_TRY(cudaMemcpyAsync(out_host, out_d, 3 * px, cudaMemcpyDeviceToHost, ctx->s_out));
+    CUDA_TRY(cudaEventRecord(ctx->u8_out_done[slot], ctx->s_out));
+    ctx->u8_used[slot] = true;
+    if (slot_out) *slot_out = slot;
     return MIGAN_OK;
+}
+
+int migan_forward_u8(migan_ctx* ctx, const uint8_t* img_host, const uint8_t* mask_host, uint8_t* out_host, int n,
+                     void* workspace, size_t workspace_bytes, int path, void* stream) {
+    int slot = 0;
+    if (int rc = forward_u8_enqueue(ctx, img_host, mask_host, out_host, n, workspace, workspace_bytes, path, stream, &slot)) return rc;
+    CUDA_TRY(cudaEventSynchronize(ctx->u8_out_done[slot]));   // out_host is complete on return
+    return MIGAN_OK;
+}
+
+int migan_forward_u8_async(migan_ctx* ctx, const uint8_t* img_host, const uint8_t* mask_host, uint8_t* out_host, int n,
+                           void* workspace, size_t workspace_bytes, int path, void* stream) {
+    return forward_u8_enqueue(ctx, img_host, mask_host, out_host, n, workspace, workspace_bytes, path, stream, nullptr);
 }
 
 int b200_preprocess_u8(const uint8_t* img, const uint8_t* mask, float* x, int n, int r, void* stream) {

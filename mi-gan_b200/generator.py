@@ -253,11 +253,13 @@ class Generator(nn.Module):
         return out
 
     @torch.no_grad()
-    def forward_u8(self, img_u8: torch.Tensor, mask_u8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward_u8(self, img_u8: torch.Tensor, mask_u8: torch.Tensor, out: Optional[torch.Tensor] = None,
+                   wait: bool = True) -> torch.Tensor:
         """uint8 request path (scripts/demo.py:56-66 + :131-142 in one call): img_u8 [N,R,R,3] RGB and mask_u8 [N,R,R]
         (255 = known) are HOST uint8 tensors (pinned for full speed); returns the composed uint8 image [N,R,R,3] on the
         host: known pixels of img, generated pixels elsewhere.  Pre/post-processing run as CUDA kernels around the forward,
-        so 7 bytes per pixel cross PCIe instead of 28."""
+        so 7 bytes per pixel cross PCIe instead of 28.  wait=False only enqueues (serving loop: submit requests back to back, then
+        `host_wait()`; the copies of request t+1 / t-1 run under the kernels of request t)."""
         r = self.resolution
         if img_u8.is_cuda or mask_u8.is_cuda or img_u8.dtype != torch.uint8 or mask_u8.dtype != torch.uint8:
             raise RuntimeError("forward_u8 expects CPU uint8 tensors")
@@ -287,8 +289,9 @@ class Generator(nn.Module):
                 eng.workspaces = {k: v for k, v in eng.workspaces.items() if k[0] == n}
                 eng.workspaces[(n, "u8")] = ws
             stream = torch.cuda.current_stream(device).cuda_stream
-            _abi.check(eng.lib.migan_forward_u8(eng.handle, img_u8.data_ptr(), mask_u8.data_ptr(), out.data_ptr(), n,
-                                                ws.data_ptr(), ws.numel(), self._path_id(), stream))
+            fn = eng.lib.migan_forward_u8 if wait else eng.lib.migan_forward_u8_async
+            _abi.check(fn(eng.handle, img_u8.data_ptr(), mask_u8.data_ptr(), out.data_ptr(), n,
+                          ws.data_ptr(), ws.numel(), self._path_id(), stream))
         return out
 
     def host_wait(self) -> None:

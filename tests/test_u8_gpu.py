@@ -57,3 +57,21 @@ def test_forward_u8_equals_composition(cuda_device, R, N):
     assert torch.equal(out[known], img[known])
     with pytest.raises(RuntimeError):
         model.forward_u8(img.float(), mask)
+
+
+def test_forward_u8_async_serving_loop(cuda_device):
+    """Back-to-back uint8 requests alternate staging slots (copies of request t+1 / t-1 under the kernels of t); every output
+    must be complete after host_wait() and equal to the synchronous call."""
+    R, N = 128, 4
+    model = migan_b200.Generator(R)
+    model.load_state_dict(O.make_state_dict(R, seed=2))
+    model = model.to(cuda_device).eval()
+    rng = np.random.RandomState(11)
+    imgs = [torch.from_numpy(rng.randint(0, 256, size=(N, R, R, 3), dtype=np.uint8)).pin_memory() for _ in range(5)]
+    masks = [torch.from_numpy(((rng.rand(N, R, R) > 0.5) * 255).astype(np.uint8)).pin_memory() for _ in range(5)]
+    outs = [torch.empty(N, R, R, 3, dtype=torch.uint8).pin_memory() for _ in range(5)]
+    for i, m, o in zip(imgs, masks, outs):
+        model.forward_u8(i, m, out=o, wait=False)
+    model.host_wait()
+    for i, m, o in zip(imgs, masks, outs):
+        assert torch.equal(o, model.forward_u8(i, m))
