@@ -230,19 +230,21 @@ SC_DEV void prestage_up(f4* __restrict__ in, const f4* __restrict__ ta, const fl
 // ---------------------------------------------------------------------------------------------------------------
 // STEM pre-stage: IN[r][c][ch] = lrelu_agc( fromrgb(x)[ch] + b[ch] ) for the chunk's 32 channels (zero outside the
 // image): EncoderBlock.fromrgb + activation, migan_inference.py:193-196, recomputed on the halo so the 64-channel
-// stem tensor never exists in HBM.  ws = [C0][4] weights * sqrt2, bs = [C0] bias * sqrt2 (shared-memory table).
+// stem tensor never exists in HBM.  ws = weights * sqrt2 pair-interleaved [C0/2][4 planes][2], bs = [C0] bias * sqrt2
+// (shared-memory table).
 // Worker item = (pixel of the 10 x 18 window, channel vector): 1440 items per chunk.
 // ---------------------------------------------------------------------------------------------------------------
 SC_DEV void prestage_stem(f4* __restrict__ in, const float* __restrict__ xa, const float* __restrict__ ws,
                           const float* __restrict__ bs, int cg0, int y0, int x0, int R, int tg) {
     const int cvec = tg & 7;
     const int ch = cg0 + cvec * 4;
-    const f4 w0 = *reinterpret_cast<const f4*>(ws + (ch + 0) * 4), w1 = *reinterpret_cast<const f4*>(ws + (ch + 1) * 4);
-    const f4 w2 = *reinterpret_cast<const f4*>(ws + (ch + 2) * 4), w3 = *reinterpret_cast<const f4*>(ws + (ch + 3) * 4);
-    const f4 bv = *reinterpret_cast<const f4*>(bs + ch);
-    const u64 wl[4] = {pk(w0.x, w1.x), pk(w0.y, w1.y), pk(w0.z, w1.z), pk(w0.w, w1.w)};   // (ch, ch+1) x input plane
-    const u64 wh[4] = {pk(w2.x, w3.x), pk(w2.y, w3.y), pk(w2.z, w3.z), pk(w2.w, w3.w)};   // (ch+2, ch+3)
-    const u64 bl = pk(bv.x, bv.y), bh = pk(bv.z, bv.w);
+    // ws is pair-interleaved: [channel pair][plane][2] = (w[ch][i], w[ch+1][i]) adjacent, so a 128-bit load is two ready pairs
+    const F4 wa = as_f4(*reinterpret_cast<const f4*>(ws + ch * 4)), wb = as_f4(*reinterpret_cast<const f4*>(ws + ch * 4 + 4));
+    const F4 wc = as_f4(*reinterpret_cast<const f4*>(ws + ch * 4 + 8)), wd = as_f4(*reinterpret_cast<const f4*>(ws + ch * 4 + 12));
+    const F4 bv = as_f4(*reinterpret_cast<const f4*>(bs + ch));
+    const P2 wl[4] = {wa.lo, wa.hi, wb.lo, wb.hi};         // (ch, ch+1) x input plane 0..3
+    const P2 wh[4] = {wc.lo, wc.hi, wd.lo, wd.hi};         // (ch+2, ch+3)
+    const P2 bl = bv.lo, bh = bv.hi;
     int r = 0, c = tg >> 3;                                // pixel (tg >> 3) + 16 k, advanced incrementally (no division)
 #pragma unroll 4
     for (int k = 0; k < 12; ++k) {

@@ -146,13 +146,18 @@ __device__ __noinline__ void mbar_timeout(int code, uint32_t parity, int* error_
     }
     __trap();
 }
+// kRelaxed: a waiter with slack (the consumers behind a double buffer) backs off between probes, so that it does not
+// compete for issue slots with the warps doing the arithmetic (round-2 ncu: a quarter of all executed instructions were probes).
+template <bool kRelaxed = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code, int* error_flag) {
     if (mbar_try_wait(bar, parity)) return;
     unsigned long long t0 = 0;
     for (;;) {
 #pragma unroll 1
-        for (int i = 0; i < 1024; ++i)
+        for (int i = 0; i < 1024; ++i) {
+            if (kRelaxed) asm volatile("nanosleep.u32 256;" ::: "memory");
             if (mbar_try_wait(bar, parity)) return;
+        }
         const unsigned long long t = globaltimer_ns();
         if (t0 == 0) t0 = t;
         else if (t - t0 > 4000000000ull) mbar_timeout(code, parity, error_flag);
@@ -320,7 +325,8 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
     }
     if (p.source == SEPCONV_SRC_STEM) {
         float* st = reinterpret_cast<float*>(smem_gen + p.off_stem);
-        for (int i = threadIdx.x; i < 4 * p.cin; i += kThreads) st[i] = __ldg(p.stem_w + i);
+        // pair-interleaved: [channel pair][plane][2] so that the pre-stage reads (w[ch][i], w[ch+1][i]) as one register pair
+        for (int i = threadIdx.x; i < 4 * p.cin; i += kThreads) st[(i >> 3) * 8 + (i & 3) * 2 + ((i >> 2) & 1)] = __ldg(p.stem_w + i);
         for (int i = threadIdx.x; i < p.cin; i += kThreads) st[4 * p.cin + i] = __ldg(p.stem_b + i);
     }
     if (warp == kMmaWarp) {  // TMEM: all 512 columns (one CTA per SM by construction)
@@ -367,7 +373,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                         for (int g = 0; g < 2; ++g) {
                             const int s = rin.stage;
                             if (p.prefetch) prefetch_next();
-                            mbar_wait(empty_in(s), rin.phase ^ 1, 100 + s, p.error_flag);
+                            mbar_wait<true>(empty_in(s), rin.phase ^ 1, 100 + s, p.error_flag);
                             rin.advance();
                             mbar_expect_tx(full_in(s), p.in_tx_bytes);
                             const uint32_t dst = smem_base + p.off_in + s * p.in_stage_stride;
@@ -499,7 +505,7 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
                             lo_tap[(a * 2 + bb) * 3 + k] = ok ? __ldg(p.img_lo + (((size_t)pimg * 3 + k) * h + iy) * w + ix) : 0.f;
                     }
             }
-            mbar_wait(full_acc(e), use_parity, 300 + e, p.error_flag);
+            mbar_wait<true>(full_acc(e), use_parity, 300 + e, p.error_flag);
             tc_fence_after();
             const float scale_g = p.inv_scale * kActGain, nz_g = nz * kActGain;
             float* out_px = p.out + (((size_t)pimg * p.H + poy) * p.W + pox) * p.cout + chan0;

@@ -141,7 +141,8 @@ def test_prestage_stem_matches_oracle(lib, y0, x0):
     b = torch.randn(C0, generator=g) * 0.1
     want = O.lrelu_agc(F.conv2d(x, w, b))
     want = F.pad(want, (1, 1, 1, 1))[0].permute(1, 2, 0).numpy()
-    ws = np.ascontiguousarray((w.numpy().reshape(C0, 4) * SQRT2).astype(np.float32))
+    ws = (w.numpy().reshape(C0, 4) * SQRT2).astype(np.float32)
+    ws = np.ascontiguousarray(ws.reshape(C0 // 2, 2, 4).transpose(0, 2, 1))      # pair-interleaved [C0/2][plane][2], as the kernel stages it
     bs = np.ascontiguousarray((b.numpy() * SQRT2).astype(np.float32))
     xn = np.ascontiguousarray(x[0].numpy())                                   # [4][R][R]
     for cg0 in (0, 32):
