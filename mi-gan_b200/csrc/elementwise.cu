@@ -505,6 +505,175 @@ cudaError_t launch_dw3x3_down_split(const float* in, const float* w9s, const flo
 
 
 // --------------------------------------------------------------------------------------
+// TMA-staged variant of dw3x3_down_split: same arithmetic per thread, but the input rows come from a shared-memory ring
+// that a producer warp fills with cp.async.bulk.tensor -- six rows (55 KB) in flight per block instead of one register row
+// per thread.  Round-2 ncu of the register-streaming kernel: 40 % of the warp time was long-scoreboard (global load) stall
+// at 24 % occupancy.  Block = (image, strip of RS low-res rows, 16 low-res columns, 64-channel slab): 256 compute threads
+// (channel pair x column pair) + 1 producer warp.  Rows / columns outside the image arrive as zeros (TMA out-of-bounds
+// fill), which is exactly the depthwise conv's zero padding.
+// --------------------------------------------------------------------------------------
+constexpr int kDownRing = 6;
+constexpr int kDownRowBytes = 36 * 64 * 4;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool down_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void down_wait(uint32_t bar, uint32_t parity) {
+    while (!down_try_wait(bar, parity)) {}
+}
+
+template <int RS>
+__global__ void __launch_bounds__(288, 2)
+dw3x3_down_tma_kernel(const __grid_constant__ DownTensorMap desc, const float* __restrict__ w9s, const float* __restrict__ biass,
+                      const float* __restrict__ fir16, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                      int C, int lw2, int lh2, int lstrips, int lslabs) {
+    constexpr float kLim = kActClamp * kActSplitScale;
+    constexpr int kRows = 2 * RS + 4;
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    __shared__ __align__(8) uint64_t s_bar[2 * kDownRing];
+    float* s_fir = reinterpret_cast<float*>(s_dyn + kDownRing * kDownRowBytes);     // [16][64] taps of this slab
+    const int W2 = 1 << lw2, H2 = 1 << lh2, H = 2 * H2;
+    uint32_t b = blockIdx.x;
+    const int slab = (int)(b & ((1u << lslabs) - 1)); b >>= lslabs;
+    const int xtile = (int)(b & ((uint32_t)(W2 >> 4) - 1)); b >>= (lw2 - 4);
+    const int strip = (int)(b & ((1u << lstrips) - 1));
+    const int img = (int)(b >> lstrips);
+    const int oy0 = strip * RS, iy_first = 2 * oy0 - 2;
+    const int cs = slab * 64;
+    const uint32_t bar0 = smem_addr(s_bar);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kDownRing; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * i), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (kDownRing + i)), "r"(8));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 16 * 64; i += 288) s_fir[i] = __ldg(fir16 + (i >> 6) * C + cs + (i & 63));
+    __syncthreads();
+
+    if (threadIdx.x >= 256) {
+        // ---- producer warp: one lane streams the rows of the slab window into the ring ----
+        if (threadIdx.x == 256) {
+            const uint64_t map = reinterpret_cast<uint64_t>(&desc);
+            for (int r = 0; r < kRows; ++r) {
+                const int st = r % kDownRing;
+                if (r >= kDownRing) down_wait(bar0 + 8u * (kDownRing + st), ((r / kDownRing) - 1) & 1);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * st), "r"(kDownRowBytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                    ::"r"(smem_addr(s_dyn + st * kDownRowBytes)), "l"(map), "r"(bar0 + 8u * st),
+                      "r"(cs), "r"(32 * xtile - 2), "r"(iy_first + r), "r"(img) : "memory");
+            }
+        }
+        return;
+    }
+
+    // ---- compute threads: (channel pair, pair of low-res columns) ----
+    const int c = (threadIdx.x & 31) * 2;                  // channel inside the slab
+    const int oxp = threadIdx.x >> 5;                      // 0..7
+    const int ox0 = xtile * 16 + 2 * oxp;
+    const bool left_ok = (ox0 > 0), right_ok = (ox0 + 2 < W2);
+    const float2* firp = reinterpret_cast<const float2*>(s_fir + c);
+    float2 wv[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wv[k] = __ldg(reinterpret_cast<const float2*>(w9s + k * C + cs + c));
+    const float2 bv = __ldg(reinterpret_cast<const float2*>(biass + cs + c));
+    const unsigned char* win = s_dyn + (4 * oxp * 64 + c) * 4;      // window column j of ring slot st: win + st * kDownRowBytes + j * 256
+
+    float2 dw[3][6];
+#pragma unroll
+    for (int s2 = 0; s2 < 3; ++s2)
+#pragma unroll
+        for (int tx = 0; tx < 6; ++tx) dw[s2][tx] = bv;
+    const float2 zero2 = make_float2(0.f, 0.f), alpha2 = make_float2(kLreluAlpha, kLreluAlpha);
+    float2 accA[2] = {zero2, zero2}, accB[2] = {zero2, zero2};
+
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const int iy = iy_first + r;
+        const int st = r % kDownRing;
+        down_wait(bar0 + 8u * st, (r / kDownRing) & 1);
+        float2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float2*>(win + st * kDownRowBytes + j * 256);
+        if (r + kDownRing < kRows) {                         // slot is refilled later: release it once this warp has read it
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8u * (kDownRing + st)) : "memory");
+        }
+#pragma unroll
+        for (int tx = 0; tx < 6; ++tx) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                dw[(r + 1) % 3][tx] = __ffma2_rn(wv[6 + kx], v[tx + kx], dw[(r + 1) % 3][tx]);
+                dw[(r + 2) % 3][tx] = __ffma2_rn(wv[3 + kx], v[tx + kx], dw[(r + 2) % 3][tx]);
+                dw[r % 3][tx] = __ffma2_rn(wv[kx], v[tx + kx], dw[r % 3][tx]);
+            }
+        }
+        if (r >= 2) {                                     // depthwise row gy = iy - 1 is complete
+            const int q = r - 2;
+            const int gy = iy - 1;
+            const int tyB = (q & 1) ? 1 : 0, tyA = tyB + 2;
+            if (gy >= 0 && gy < H) {
+#pragma unroll
+                for (int tx = 0; tx < 6; ++tx) {
+                    if ((tx == 0 && !left_ok) || (tx == 5 && !right_ok)) continue;   // depthwise column outside the image: zero
+                    const float2 a = dw[(r + 1) % 3][tx], bb = __fmul2_rn(a, alpha2);
+                    const float2 d = make_float2(fminf(fmax3f(a.x, bb.x, -kLim), kLim), fminf(fmax3f(a.y, bb.y, -kLim), kLim));
+                    if (tx < 4) {
+                        accB[0] = __ffma2_rn(firp[(tyB * 4 + tx) * 32], d, accB[0]);
+                        accA[0] = __ffma2_rn(firp[(tyA * 4 + tx) * 32], d, accA[0]);
+                    }
+                    if (tx >= 2) {
+                        accB[1] = __ffma2_rn(firp[(tyB * 4 + tx - 2) * 32], d, accB[1]);
+                        accA[1] = __ffma2_rn(firp[(tyA * 4 + tx - 2) * 32], d, accA[1]);
+                    }
+                }
+            }
+            if ((q & 1) && q >= 3) {
+                const int orow = oy0 + ((q - 3) >> 1);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const size_t o = (((size_t)img * H2 + orow) * W2 + ox0 + e) * (size_t)C + cs + c;
+                    const float2 ov = accA[e];
+                    const __half2 h = __floats2half2_rn(ov.x, ov.y);
+                    const float2 hf = __half22float2(h);
+                    *reinterpret_cast<__half2*>(out_hi + o) = h;
+                    *reinterpret_cast<__half2*>(out_lo + o) = __floats2half2_rn(ov.x - hf.x, ov.y - hf.y);
+                }
+            }
+            if (q & 1) { accA[0] = accB[0]; accA[1] = accB[1]; accB[0] = zero2; accB[1] = zero2; }
+        }
+#pragma unroll
+        for (int tx = 0; tx < 6; ++tx) dw[(r + 1) % 3][tx] = bv;
+    }
+}
+
+cudaError_t launch_dw3x3_down_tma(const DownTensorMap& desc, const float* w9s, const float* biass, const float* fir16,
+                                  __half* out_hi, __half* out_lo, int n, int H, int W, int C, cudaStream_t s) {
+    const int H2 = H / 2, W2 = W / 2;
+    if (W2 < 16 || (W2 & (W2 - 1)) || C % 64 != 0) return cudaErrorInvalidValue;
+    const int rs = (H2 >= 8) ? 8 : 4, strips = H2 / rs, slabs = C / 64;
+    if (strips < 1 || (slabs & (slabs - 1))) return cudaErrorInvalidValue;
+    const size_t blocks = (size_t)n * strips * (W2 / 16) * slabs;
+    if (blocks == 0 || blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)kDownRing * kDownRowBytes + 16 * 64 * sizeof(float);
+    static bool attr_set[2] = {false, false};
+    auto kern = (rs == 8) ? dw3x3_down_tma_kernel<8> : dw3x3_down_tma_kernel<4>;
+    if (!attr_set[rs == 8]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set[rs == 8] = true;
+    }
+    kern<<<(unsigned)blocks, 288, smem, s>>>(desc, w9s, biass, fir16, out_hi, out_lo, C, host_log2(W2), host_log2(H2),
+                                             host_log2(strips), host_log2(slabs));
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
 // 2x FIR up-sampling (polyphase: only the taps that meet a non-zero of the zero-inserted
 // signal) + noise + act + skip.  out[o] = sum_t f[t] * z[o + t - 2], z[2i] = x[i], z[odd] = 0.
 // --------------------------------------------------------------------------------------

@@ -30,6 +30,13 @@ cudaError_t launch_dw3x3_down(const float* in, const float* w9, const float* bia
 // pre-multiplied by kActSplitScale * sqrt(2); C in {64, 128, 256, 512}.
 cudaError_t launch_dw3x3_down_split(const float* in, const float* w9s, const float* biass, const float* fir16,
                                     __half* out_hi, __half* out_lo, int n, int H, int W, int C, cudaStream_t s);
+// TMA-staged variant (W/2 >= 16): a producer warp streams the input rows of a (64-channel, 36-column) slab into a shared-memory
+// ring with cp.async.bulk.tensor (out-of-image rows / columns arrive zero-filled), so the row walk never waits on global
+// memory.  `desc` = 128-byte CUtensorMap of the input made by make_down_tensor_map (host, once per plan).
+struct alignas(64) DownTensorMap { unsigned char bytes[128]; };
+const char* make_down_tensor_map(DownTensorMap* desc, const float* in, int n, int H, int W, int C);   // sepconv_tc.cu (driver entry point lives there)
+cudaError_t launch_dw3x3_down_tma(const DownTensorMap& desc, const float* w9s, const float* biass, const float* fir16,
+                                  __half* out_hi, __half* out_lo, int n, int H, int W, int C, cudaStream_t s);
 // 2x polyphase FIR up-sampling of the raw 1x1-conv output + noise + lrelu_agc + skip add.
 // t [n,h,w,C] -> out [n,2h,2w,C]; fir16 [16][C] (gain included); noise [2h*2w] (already
 // multiplied by noise_strength) or null; skip [n,2h,2w,C] or null (added AFTER the activation).

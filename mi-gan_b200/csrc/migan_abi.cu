@@ -113,6 +113,8 @@ struct Step {
     int act = 0;
     bool want_f32 = false;
     migan::SepconvTcArgs tc;  // resolved tcgen05 launch (tensor maps, tiling)
+    migan::DownTensorMap down_map;   // K_DWDOWN on the TMA-staged kernel: tensor map of the input
+    bool down_tma = false;
     // roofline bookkeeping: algorithmic bytes = own input(s) read once + output written once
     std::string label;
     double alg_bytes = 0, flops = 0;
@@ -601,6 +603,10 @@ struct PlanBuilder {
         s.tap = name; s.tap_src = src; s.tapC = C; s.tapH = H; s.tapW = W; s.tap_planar = planar; s.tap_flags = flags;
     }
 
+    static bool down_tma_enabled() {    // MIGAN_DOWN_TMA=0: register-streaming kernel (A/B measurements)
+        const char* e = getenv("MIGAN_DOWN_TMA");
+        return !e || atoi(e) != 0;
+    }
     static int fuse_mask_dw() {         // MIGAN_FUSE bit 2: run the depthwise stage of the small Cout = 512 levels (res <= 32) inside the
         return fuse_mask() & 4;         // tensor-core kernel (its prologue repeats per N tile, which is cheap there) instead of as its own launch
     }
@@ -626,6 +632,11 @@ struct PlanBuilder {
                 s.hi = reinterpret_cast<__half*>(S[t1]);
                 s.lo = s.hi + (size_t)n * L.res_pw * L.res_pw * L.cin;
                 ghi = s.hi; glo = s.lo;
+                if (L.res_pw >= 16 && down_tma_enabled()) {   // rows staged through shared memory by TMA (elementwise.cu)
+                    if (const char* err = migan::make_down_tensor_map(&s.down_map, in, n, L.res_in, L.res_in, L.cin))
+                        return fail(MIGAN_ERR_CUDA, "tensor map for %sdownsample failed: %s", L.p.c_str(), err);
+                    s.down_tma = true;
+                }
             } else {
                 s.out = S[t1]; gemm_in = S[t1];
                 set_tap(s, L.p + "down", S[t1], L.cin, L.res_pw, L.res_pw);
@@ -848,7 +859,9 @@ int run_step(migan_ctx* ctx, Step& s, const float* x, float* y, cudaStream_t st)
             e = migan::launch_dw3x3(in, s.L->w9, s.L->bias, s.out, s.hi, s.lo, s.n, s.H, s.W, s.C, st);
             break;
         case K_DWDOWN:
-            if (s.hi && !s.out && s.W >= 8)   // tensor-core feed: specialised kernel on the pre-scaled tap table
+            if (s.down_tma)
+                e = migan::launch_dw3x3_down_tma(s.down_map, s.L->w9_tc, s.L->bias_tc, s.L->fir16, s.hi, s.lo, s.n, s.H, s.W, s.C, st);
+            else if (s.hi && !s.out && s.W >= 8)   // tensor-core feed: specialised kernel on the pre-scaled tap table
                 e = migan::launch_dw3x3_down_split(in, s.L->w9_tc, s.L->bias_tc, s.L->fir16, s.hi, s.lo, s.n, s.H, s.W, s.C, st);
             else
                 e = migan::launch_dw3x3_down(in, s.L->w9, s.L->bias, s.L->fir16, s.out, s.hi, s.lo, s.n, s.H, s.W, s.C, st);

@@ -234,8 +234,9 @@ SC_DEV void prestage_up(f4* __restrict__ in, const f4* __restrict__ ta, const fl
 // (shared-memory table).
 // Worker item = (pixel of the 10 x 18 window, channel vector): 1440 items per chunk.
 // ---------------------------------------------------------------------------------------------------------------
-SC_DEV void prestage_stem(f4* __restrict__ in, const float* __restrict__ xa, const float* __restrict__ ws,
-                          const float* __restrict__ bs, int cg0, int y0, int x0, int R, int tg) {
+template <bool kBorder>
+SC_DEV void prestage_stem_t(f4* __restrict__ in, const float* __restrict__ xa, const float* __restrict__ ws,
+                            const float* __restrict__ bs, int cg0, int y0, int x0, int R, int tg) {
     const int cvec = tg & 7;
     const int ch = cg0 + cvec * 4;
     // ws is pair-interleaved: [channel pair][plane][2] = (w[ch][i], w[ch+1][i]) adjacent, so a 128-bit load is two ready pairs
@@ -263,9 +264,15 @@ SC_DEV void prestage_stem(f4* __restrict__ in, const float* __restrict__ xa, con
         F4 o;
         o.lo = act_pair(lo, kClamp);
         o.hi = act_pair(hi, kClamp);
-        if (!((Y >= 0) && (Y < R) && (X >= 0) && (X < R))) { o.lo = p2zero(); o.hi = p2zero(); }
+        if (kBorder && !((Y >= 0) && (Y < R) && (X >= 0) && (X < R))) { o.lo = p2zero(); o.hi = p2zero(); }
         in[px * 8 + cvec] = to_f4(o);
     }
+}
+// Tiles that touch the image border zero the halo pixels outside the image; interior tiles (most of them) skip the test.
+SC_DEV void prestage_stem(f4* __restrict__ in, const float* __restrict__ xa, const float* __restrict__ ws,
+                          const float* __restrict__ bs, int cg0, int y0, int x0, int R, int tg) {
+    if (y0 == 0 || x0 == 0 || y0 + 8 == R || x0 + 16 == R) prestage_stem_t<true>(in, xa, ws, bs, cg0, y0, x0, R, tg);
+    else prestage_stem_t<false>(in, xa, ws, bs, cg0, y0, x0, R, tg);
 }
 
 }  // namespace stages

@@ -724,6 +724,15 @@ int env_int(const char* name, int dflt) {
 // Params is kept opaque to the ABI layer: SepconvTcArgs carries it as bytes.
 static_assert(sizeof(Params) <= sizeof(((SepconvTcArgs*)0)->params_blob), "params blob too small");
 
+// Tensor map of an NHWC fp32 tensor for the TMA-staged down-sampling kernel (elementwise.cu): box = 64 channels x 36 columns x 1 row.
+const char* make_down_tensor_map(DownTensorMap* desc, const float* in, int n, int H, int W, int C) {
+    static_assert(sizeof(CUtensorMap) <= sizeof(DownTensorMap), "tensor map size");
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+    const uint32_t box[4] = {64u, 36u, 1u, 1u};
+    return encode_map(reinterpret_cast<CUtensorMap*>(desc), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
 cudaError_t configure_sepconv_tc() {
     cudaError_t e = cudaFuncSetAttribute(sepconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - kStaticSmem));
     if (e != cudaSuccess) return e;
