@@ -370,10 +370,33 @@ def run_b200(args):
                                "GBps": sum(b["alg_bytes"] for b in by_kernel.values()) / (total_ms * 1e-3) / 1e9},
                 "by_kernel": {k: {"ms": round(b["ms"], 4), "GBps": round(b["alg_bytes"] / (b["ms"] * 1e-3) / 1e9, 1),
                                   "launches": b["launches"]} for k, b in by_kernel.items()}}
+    if R == 512:   # fully fused ideal = 1094.7 MB per image at 512 x 512 (every layer reads its input and writes its output once)
+        ideal = 1094.7e6 * B
+        roofline["whole_step"]["fused_ideal_bytes"] = ideal
+        roofline["whole_step"]["frac_of_peak_vs_fused_ideal"] = ideal / (elapsed_ms / K * 1e-3) / 1e9 / peak if world == 1 else None
     if args.profile_out:
         os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
         with open(args.profile_out, "w") as f:
             json.dump({"res": R, "batch": B, "path": args.path, "hbm_peak_GBps": peak, "launches": table}, f, indent=1)
+
+    # ---- batch-1 latency through the CUDA-graph replay (the reference's primary caller is batch 1, scripts/demo.py:125-142) ----
+    latency = None
+    if world == 1:
+        try:
+            x1 = x[:1].contiguous()
+            for _ in range(5):
+                model(x1)
+            torch.cuda.synchronize(dev)
+            lat = []
+            for _ in range(50):
+                t0 = time.perf_counter()
+                model(x1)
+                torch.cuda.synchronize(dev)
+                lat.append((time.perf_counter() - t0) * 1e3)
+            latency = {"batch": 1, "p50_ms": statistics.median(lat), "p90_ms": sorted(lat)[44], "api": "Generator.forward (migan_forward_graph)",
+                       "launches_replayed": model.last_launch_count()}
+        except Exception as exc:
+            latency = {"error": str(exc)[:200]}
 
     cpu = None
     parity = None
@@ -411,6 +434,7 @@ def run_b200(args):
                           ("K host shards per rank through ShardedGenerator.forward_host_async: pinned H2D, forward, all-gather, D2H of the "
                            "rank's rows of the gathered tensor; copies of batch t+1 / t-1 run under the kernels of batch t")},
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8,
+        "latency_bs1": latency,
         "gpu_launches": launches_per_step * K,
     }
     print_json(json.dumps(line), flush=True)

@@ -112,6 +112,13 @@ int b200_preprocess_u8(const uint8_t* img_hwc, const uint8_t* mask_hw, float* x_
 int b200_postprocess_u8(const float* y_nchw, const uint8_t* img_hwc, const uint8_t* mask_hw, uint8_t* out_hwc, int n, int r,
                         void* stream);
 
+/* Feathered composite of the deployed (ONNX) pipeline, scripts/create_onnx_pipeline.py:233-245, for a crop at the model
+ * resolution (DEVICE pointers, NCHW like the pipeline): blend weight = 5x5 smoothing (reflect border) of the 3x3 max-pooled
+ * mask / 255; out = clamp(image * w + ((y*0.5+0.5)*255).clamp(0,255) * (1 - w), 0, 255) -> uint8.  k25 = the 25 smoothing
+ * taps on the HOST (the GaussianSmoothing buffer of :66-88; migan_b200.ops.feather_kernel() builds it the same way). */
+int b200_feather_composite(const float* y_nchw, const uint8_t* image_nchw, const uint8_t* mask_n1hw, uint8_t* out_nchw,
+                           int n, int H, int W, const float* k25_host, void* stream);
+
 /* Kernels launched by the most recent migan_forward on this context. */
 int migan_last_launch_count(const migan_ctx* ctx);
 

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace migan {
 
@@ -44,6 +45,29 @@ __device__ __forceinline__ void split_f16(float v, float scale, __half& hi, __ha
     float s = v * scale;
     hi = __float2half_rn(s);
     lo = __float2half_rn(s - __half2float(hi));
+}
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start while
+// its predecessor in the stream is still draining; everything before pdl_wait() (barrier / TMEM setup, weight-table loads --
+// nothing the predecessor writes) overlaps the predecessor's tail, everything after it sees the predecessor's memory.
+// pdl_trigger() lets the successor's blocks start launching as soon as every block of this grid has passed it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Host: kernel launch with the PDL attribute (MIGAN_PDL=0 turns the attribute off for A/B measurements).
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("MIGAN_PDL"); return !e || atoi(e) != 0; }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 }  // namespace migan

@@ -34,6 +34,8 @@ __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 __global__ void __launch_bounds__(256)
 stem_fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                     float* __restrict__ out, uint32_t items, int lhw, int lcv) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t idx = blockIdx.x * 256u + threadIdx.x;     // over (pixel quads) x (channel quads)
     if (idx >= items) return;
     const uint32_t c4 = idx & ((1u << lcv) - 1);
@@ -85,8 +87,8 @@ cudaError_t launch_stem(const float* x, const float* w, const float* b, float* o
     const size_t per_img = (size_t)H * W / 4 * (C0 / 4);
     return for_image_groups(n, per_img, [&](int i0, int cnt) {
         const uint32_t items = (uint32_t)(per_img * cnt);
-        stem_fromrgb_kernel<<<(items + 255) / 256, 256, 0, s>>>(x + (size_t)i0 * 4 * H * W, w, b, out + (size_t)i0 * H * W * C0,
-                                                               items, host_log2(H * W), host_log2(C0 / 4));
+        launch_pdl(stem_fromrgb_kernel, dim3((items + 255) / 256), dim3(256), 0, s, x + (size_t)i0 * 4 * H * W, w, b, out + (size_t)i0 * H * W * C0,
+                   items, host_log2(H * W), host_log2(C0 / 4));
     });
 }
 
@@ -124,6 +126,8 @@ __global__ void __launch_bounds__(256)
 dw3x3_act_kernel(const float* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ bias,
                  float* __restrict__ out, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                  uint32_t items, int lw, int lh, int lcp, int lstrips) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
     if (idx >= items) return;
     const int W = 1 << lw, H = 1 << lh, C = 2 << lcp;
@@ -189,9 +193,8 @@ cudaError_t launch_dw3x3(const float* in, const float* w9, const float* bias, fl
         const uint32_t items = (uint32_t)(per_img * cnt);
         const size_t off = (size_t)i0 * H * W * C;
         auto kern = (rs == 8) ? dw3x3_act_kernel<8> : dw3x3_act_kernel<4>;
-        kern<<<(items + 255) / 256, 256, 0, s>>>(in + off, w9, bias, out ? out + off : nullptr, out_hi ? out_hi + off : nullptr,
-                                                out_lo ? out_lo + off : nullptr, items, host_log2(W), host_log2(H), host_log2(C / 2),
-                                                host_log2(strips));
+        launch_pdl(kern, dim3((items + 255) / 256), dim3(256), 0, s, in + off, w9, bias, out ? out + off : nullptr, out_hi ? out_hi + off : nullptr,
+                   out_lo ? out_lo + off : nullptr, items, host_log2(W), host_log2(H), host_log2(C / 2), host_log2(strips));
     });
 }
 
@@ -380,7 +383,9 @@ dw3x3_down_split_kernel(const float* __restrict__ in, const float* __restrict__ 
     const int oy0 = strip * RS;
 
     extern __shared__ float s_fir[];                       // [16][C]
+    pdl_trigger();
     for (int i = threadIdx.x; i < 16 * C; i += 256) s_fir[i] = __ldg(fir16 + i);
+    pdl_wait();                                            // the taps are weights; the input is the predecessor's output
     __syncthreads();
     if (idx >= items) return;
     const float2* firp = reinterpret_cast<const float2*>(s_fir + c);
@@ -474,8 +479,8 @@ dw3x3_down_split_kernel(const float* __restrict__ in, const float* __restrict__ 
 template <int RS, int C>
 static void launch_down_split_inst(const float* in, const float* w9s, const float* biass, const float* fir16, __half* hi, __half* lo,
                                    uint32_t items, int W2, int H2, int strips, cudaStream_t s) {
-    dw3x3_down_split_kernel<RS, C><<<(items + 255) / 256, 256, 16 * C * sizeof(float), s>>>(in, w9s, biass, fir16, hi, lo, items,
-                                                                                           host_log2(W2), host_log2(H2), host_log2(strips));
+    launch_pdl(dw3x3_down_split_kernel<RS, C>, dim3((items + 255) / 256), dim3(256), 16 * C * sizeof(float), s, in, w9s, biass, fir16, hi, lo, items,
+               host_log2(W2), host_log2(H2), host_log2(strips));
 }
 
 // w9s / biass: depthwise taps and bias * kActSplitScale * sqrt(2).  C in {64, 128, 256, 512}.
@@ -552,7 +557,9 @@ dw3x3_down_tma_kernel(const __grid_constant__ DownTensorMap desc, const float* _
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_trigger();
     for (int i = threadIdx.x; i < 16 * 64; i += 288) s_fir[i] = __ldg(fir16 + (i >> 6) * C + cs + (i & 63));
+    pdl_wait();                                            // barriers and taps are set up under the predecessor's tail
     __syncthreads();
 
     if (threadIdx.x >= 256) {
@@ -668,9 +675,8 @@ cudaError_t launch_dw3x3_down_tma(const DownTensorMap& desc, const float* w9s, c
         if (e != cudaSuccess) return e;
         attr_set[rs == 8] = true;
     }
-    kern<<<(unsigned)blocks, 288, smem, s>>>(desc, w9s, biass, fir16, out_hi, out_lo, C, host_log2(W2), host_log2(H2),
-                                             host_log2(strips), host_log2(slabs));
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3((unsigned)blocks), dim3(288), smem, s, desc, w9s, biass, fir16, out_hi, out_lo, C, host_log2(W2), host_log2(H2),
+                      host_log2(strips), host_log2(slabs));
 }
 
 // --------------------------------------------------------------------------------------
@@ -685,7 +691,9 @@ up2_noise_act_skip_kernel(const float* __restrict__ t, const float* __restrict__
                           float* __restrict__ out, uint32_t items, int lw, int lh, int lcv) {
     extern __shared__ float4 s_taps[];                    // [16][C/4]
     const int w = 1 << lw, h = 1 << lh, W2 = 2 * w, C = 4 << lcv, CV = 1 << lcv;
+    pdl_trigger();
     for (int i = threadIdx.x; i < 16 * CV; i += 256) s_taps[i] = ldg4(fir16 + i * 4);
+    pdl_wait();
     __syncthreads();
     const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
     if (idx >= items) return;
@@ -736,8 +744,8 @@ cudaError_t launch_up2(const float* t, const float* fir16, const float* noise, c
     return for_image_groups(n, per_img, [&](int i0, int cnt) {
         const uint32_t items = (uint32_t)(per_img * cnt);
         const size_t oi = (size_t)i0 * h * w * C, oo = (size_t)i0 * 4 * h * w * C;
-        up2_noise_act_skip_kernel<<<(items + 255) / 256, 256, 16 * C * sizeof(float), s>>>(
-            t + oi, fir16, noise, skip ? skip + oo : nullptr, out + oo, items, host_log2(w), host_log2(h), host_log2(C / 4));
+        launch_pdl(up2_noise_act_skip_kernel, dim3((items + 255) / 256), dim3(256), 16 * C * sizeof(float), s,
+                   t + oi, fir16, noise, skip ? skip + oo : nullptr, out + oo, items, host_log2(w), host_log2(h), host_log2(C / 4));
     });
 }
 
@@ -750,6 +758,8 @@ __global__ void __launch_bounds__(256)
 torgb_img_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                  const float* __restrict__ img_lo, const float* __restrict__ fir, float* __restrict__ img_out,
                  int64_t npix, int r, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int sub = lane % G;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -807,10 +817,10 @@ cudaError_t launch_torgb(const float* x, const float* w, const float* b, const f
     const int64_t npix = (int64_t)n * r * r;
     if (C / 4 >= 32) {
         const int64_t threads = npix * 32;
-        torgb_img_kernel<32><<<blocks_for(threads, 256), 256, 0, s>>>(x, w, b, img_lo, fir16x3, img_out, npix, r, C);
+        launch_pdl(torgb_img_kernel<32>, dim3(blocks_for(threads, 256)), dim3(256), 0, s, x, w, b, img_lo, fir16x3, img_out, npix, r, C);
     } else {
         const int64_t threads = npix * 16;
-        torgb_img_kernel<16><<<blocks_for(threads, 256), 256, 0, s>>>(x, w, b, img_lo, fir16x3, img_out, npix, r, C);
+        launch_pdl(torgb_img_kernel<16>, dim3(blocks_for(threads, 256)), dim3(256), 0, s, x, w, b, img_lo, fir16x3, img_out, npix, r, C);
     }
     return cudaGetLastError();
 }
@@ -818,6 +828,8 @@ cudaError_t launch_torgb(const float* x, const float* w, const float* b, const f
 // --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 add_inplace_kernel(float* __restrict__ x, const float* __restrict__ y, int64_t n4) {
+    pdl_trigger();
+    pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4 a = reinterpret_cast<float4*>(x)[i];
@@ -827,7 +839,7 @@ add_inplace_kernel(float* __restrict__ x, const float* __restrict__ y, int64_t n
 }
 
 cudaError_t launch_add(float* x, const float* y, int64_t numel, cudaStream_t s) {
-    add_inplace_kernel<<<blocks_for(numel / 4, 256), 256, 0, s>>>(x, y, numel / 4);
+    launch_pdl(add_inplace_kernel, dim3(blocks_for(numel / 4, 256)), dim3(256), 0, s, x, y, numel / 4);
     return cudaGetLastError();
 }
 

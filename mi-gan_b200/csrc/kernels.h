@@ -64,6 +64,9 @@ cudaError_t launch_bias_act(const float* x, const float* b, float* y, int64_t nu
                             int act, float alpha, float gain, float clamp, cudaStream_t s);
 
 // ---- uint8 pre/post-processing (prepost.cu): demo.py:56-66 and :135-142 around the forward ------
+// feathered composite of the ONNX pipeline (create_onnx_pipeline.py:233-245): NCHW uint8 image / mask, 25 smoothing taps (host array)
+int launch_feather_composite(const float* y_nchw, const uint8_t* img_nchw, const uint8_t* mask_n1hw, uint8_t* out_nchw, int n, int H, int W,
+                             const float* k25_host, cudaStream_t s);
 int launch_preprocess_u8(const uint8_t* img_hwc, const uint8_t* mask_hw, float* x_nchw, int n, int r, cudaStream_t s);
 int launch_postprocess_u8(const float* y_nchw, const uint8_t* img_hwc, const uint8_t* mask_hw, uint8_t* out_hwc, int n, int r,
                           cudaStream_t s);

@@ -1217,6 +1217,14 @@ int b200_postprocess_u8(const float* y, const uint8_t* img, const uint8_t* mask,
     return MIGAN_OK;
 }
 
+int b200_feather_composite(const float* y, const uint8_t* img, const uint8_t* mask, uint8_t* out, int n, int H, int W,
+                           const float* k25, void* stream) {
+    if (!y || !img || !mask || !out || !k25) return fail(MIGAN_ERR_INVALID, "feather_composite: null argument");
+    if (n <= 0 || H < 3 || W < 3) return fail(MIGAN_ERR_INVALID, "feather_composite: need n >= 1 and H, W >= 3 (reflect padding of 2), got %d x %d x %d", n, H, W);
+    CUDA_TRY((cudaError_t)migan::launch_feather_composite(y, img, mask, out, n, H, W, k25, static_cast<cudaStream_t>(stream)));
+    return MIGAN_OK;
+}
+
 int migan_host_wait(migan_ctx* ctx) {
     if (!ctx) return fail(MIGAN_ERR_INVALID, "null ctx");
     if (!ctx->s_out) return MIGAN_OK;

@@ -329,10 +329,12 @@ sepconv_tc_kernel(const __grid_constant__ Params p) {
         for (int i = threadIdx.x; i < 4 * p.cin; i += kThreads) st[(i >> 3) * 8 + (i & 3) * 2 + ((i >> 2) & 1)] = __ldg(p.stem_w + i);
         for (int i = threadIdx.x; i < p.cin; i += kThreads) st[4 * p.cin + i] = __ldg(p.stem_b + i);
     }
+    pdl_trigger();           // the successor's blocks may start their own setup as soon as SMs free up
     if (warp == kMmaWarp) {  // TMEM: all 512 columns (one CTA per SM by construction)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_wait();              // barriers, TMEM and the weight tables above are set up under the predecessor's tail; its output is read below
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -960,8 +962,7 @@ cudaError_t launch_sepconv_tc(SepconvTcArgs& a, cudaStream_t s, float* img_out_o
     Params p;
     memcpy(&p, a.params_blob, sizeof(p));
     if (img_out_override) p.img_out = img_out_override;
-    sepconv_tc_kernel<<<a.grid, kThreads, a.smem_bytes, s>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(sepconv_tc_kernel, dim3(a.grid), dim3(kThreads), a.smem_bytes, s, p);
 }
 
 }  // namespace migan

@@ -275,3 +275,36 @@ def postprocess_u8(y: torch.Tensor, img_u8: torch.Tensor, mask_u8: torch.Tensor)
         _abi.check(_abi.load().b200_postprocess_u8(y.data_ptr(), img_u8.data_ptr(), mask_u8.data_ptr(), out.data_ptr(), n, r,
                                                    _stream(y)))
     return out
+
+
+def feather_kernel(kernel_size: int = 5, sigma: float = 1.0) -> torch.Tensor:
+    """The smoothing kernel of the deployed pipeline's GaussianSmoothing (scripts/create_onnx_pipeline.py:66-88), built with the
+    same torch expression so that it is bit-identical to the buffer the reference registers (5x5, sigma 1 at :127-128)."""
+    import math
+    grids = torch.meshgrid([torch.arange(kernel_size, dtype=torch.float32) for _ in range(2)], indexing="ij")
+    kernel = 1
+    mean = (kernel_size - 1) / 2
+    for g in grids:
+        kernel = kernel * (1 / (sigma * math.sqrt(2 * math.pi)) * torch.exp(-((g - mean) / (2 * sigma)) ** 2))
+    return (kernel / torch.sum(kernel)).contiguous()
+
+
+def feather_composite(y: torch.Tensor, image_u8: torch.Tensor, mask_u8: torch.Tensor, kernel: torch.Tensor = None) -> torch.Tensor:
+    """uint8 [N,3,H,W] = the feathered blend of the deployed pipeline (scripts/create_onnx_pipeline.py:233-245) of the generator
+    output y [N,3,H,W] (float32, CUDA) with image_u8 [N,3,H,W] under mask_u8 [N,1,H,W] (255 = known), all at the same size:
+    the mask is dilated (3x3 max-pool), smoothed (5x5, reflect border) and used as the per-pixel weight."""
+    y = _require_cuda_f32(y, "y")
+    n, h, w = y.shape[0], y.shape[2], y.shape[3]
+    if tuple(y.shape) != (n, 3, h, w) or tuple(image_u8.shape) != (n, 3, h, w) or tuple(mask_u8.shape) != (n, 1, h, w):
+        raise RuntimeError("feather_composite expects y [N,3,H,W], image [N,3,H,W], mask [N,1,H,W]")
+    if not (image_u8.is_cuda and mask_u8.is_cuda) or image_u8.dtype != torch.uint8 or mask_u8.dtype != torch.uint8:
+        raise RuntimeError("feather_composite expects uint8 CUDA tensors: migan_b200.ops has no CPU path")
+    k = (feather_kernel() if kernel is None else kernel).detach().to("cpu", torch.float32).contiguous()
+    if k.numel() != 25:
+        raise RuntimeError("feather_composite implements the pipeline's 5x5 smoothing kernel (25 taps)")
+    image_u8, mask_u8 = image_u8.contiguous(), mask_u8.contiguous()
+    out = torch.empty((n, 3, h, w), dtype=torch.uint8, device=y.device)
+    with _guard(y.device):
+        _abi.check(_abi.load().b200_feather_composite(y.data_ptr(), image_u8.data_ptr(), mask_u8.data_ptr(), out.data_ptr(), n, h, w,
+                                                      k.data_ptr(), _stream(y)))
+    return out

@@ -70,14 +70,16 @@ class ShardedGenerator:
 
     gather = "nccl": one `all_gather_into_tensor` per batch (NCCL's copy kernels, SM-resident).
     gather = "ce" (CUDA tensors, all ranks on one box): the same all-gather with the bytes moved by the copy engines.  Every
-      rank publishes a small ring of output buffers to its peers once (CUDA IPC, through torch's tensor sharing); per batch
-      it (1) puts its y into the ring, (2) joins an 8-byte NCCL all-reduce -- the only collective kernel, used as the "every
-      rank's y is in place" signal -- and (3) pulls the 7 peer shards into a fresh gathered tensor with peer-to-peer
-      `cudaMemcpyAsync` reads over NVLink on a side stream.  No SM is taken from the compute kernels, so nothing has to be
-      reserved for the collective, and the pull of batch t overlaps the compute of batch t+1.
+      rank publishes a ring of RING gathered-output buffers to its peers once (CUDA IPC, through torch's tensor sharing); per
+      batch it (1) writes its rows into the current slot of every rank's ring with peer-to-peer `cudaMemcpyAsync` over NVLink
+      (one stream per peer), then (2) joins an 8-byte NCCL all-reduce -- the only collective kernel -- whose completion means
+      "every rank's rows have landed here".  No SM is taken from the compute kernels, so nothing has to be reserved for the
+      collective, and the transfer of batch t overlaps the compute of batch t+1.  LIFETIME: `forward_async` returns a view of
+      the ring; it stays valid until RING - 1 further `forward_async` calls (consume or clone it before).  `forward` /
+      `forward_global` return a private copy.
     gather = "auto": "ce" when possible, else "nccl"."""
 
-    RING = 3   # published y buffers per rank: slot t % RING is rewritten only after the ready signal of step t - RING + 1
+    RING = 4   # gathered buffers per rank (copy-engine path): the tensor of step t is valid until forward_async(t + RING - 1)
 
     def __init__(self, model: Callable[[torch.Tensor], torch.Tensor], group: Optional[dist.ProcessGroup] = None,
                  gather: str = "auto"):
@@ -110,9 +112,10 @@ class ShardedGenerator:
 
     # -- copy-engine all-gather ---------------------------------------------------------------------------------------
     def _setup_ce(self, y: torch.Tensor):
-        """Publish RING output buffers of y's shape to every peer and map theirs (one-time, collective)."""
+        """Publish RING gathered-output buffers to every peer and map theirs (one-time, collective)."""
         from torch.multiprocessing.reductions import reduce_tensor
-        ring = [torch.empty_like(y) for _ in range(self.RING)]
+        n = y.shape[0]
+        ring = [torch.empty((self.world_size * n,) + tuple(y.shape[1:]), dtype=y.dtype, device=y.device) for _ in range(self.RING)]
         mine = [reduce_tensor(t) for t in ring]                       # (rebuild_fn, args): CUDA IPC handle + offset
         everyone = [None] * self.world_size
         dist.all_gather_object(everyone, mine, group=self.group)
@@ -120,35 +123,46 @@ class ShardedGenerator:
         for p in range(self.world_size):
             if p != self.rank:
                 peers[p] = [fn(*args) for fn, args in everyone[p]]    # tensors aliasing rank p's ring (peer-mapped)
-                if tuple(peers[p][0].shape) != tuple(y.shape):
-                    raise RuntimeError("rank %d published shards of a different shape" % p)
+                if tuple(peers[p][0].shape) != tuple(ring[0].shape):
+                    raise RuntimeError("rank %d published buffers of a different shape" % p)
         self._ce = {"ring": ring, "peers": peers, "side": torch.cuda.Stream(device=y.device),
-                    "flag": torch.zeros(1, device=y.device), "ready": {}, "shape": tuple(y.shape)}
+                    "push": {p: torch.cuda.Stream(device=y.device) for p in peers},
+                    "flag": torch.zeros(1, device=y.device), "ready": None, "shape": tuple(y.shape)}
 
     def _forward_ce(self, y: torch.Tensor) -> GatherHandle:
+        """Push form: this rank writes its rows into slot t % RING of EVERY rank's gathered ring (posted peer-to-peer writes,
+        one stream per peer so several copy engines / NVLink ports work at once), then joins the 8-byte all-reduce.  Its
+        completion on a rank means every rank's rows have landed there.  Slot t % RING was last handed out at step t - RING and,
+        by the lifetime rule of `forward_async`, is no longer in use once its owner has CALLED forward_async(t - 1) -- which is
+        what the completed ready signal of step t - 1 certifies for every rank."""
         ce, t, n = self._ce, self._step, y.shape[0]
         slot = t % self.RING
         cur = torch.cuda.current_stream(y.device)
-        old = ce["ready"].pop(t - self.RING + 1, None)
-        if old is not None:
-            old.wait()                                # slot's previous content (step t - RING) has been pulled by every peer
-        ce["ring"][slot].copy_(y, non_blocking=True)
-        out = torch.empty((self.world_size * n,) + tuple(y.shape[1:]), dtype=y.dtype, device=y.device)
         ev = torch.cuda.Event()
         ev.record(cur)
         side = ce["side"]
+        rows = slice(self.rank * n, (self.rank + 1) * n)
         with torch.cuda.stream(side):
             side.wait_event(ev)
-            ready = dist.all_reduce(ce["flag"], group=self.group, async_op=True)   # "every rank's y(t) is in its ring"
-            ready.wait()                              # the side stream (not the host) waits for it
+            if ce["ready"] is not None:
+                ce["ready"].wait()                    # step t-1's signal: every rank is past its use of this slot
+            base = torch.cuda.Event()
+            base.record(side)
+            ce["ring"][slot][rows].copy_(y, non_blocking=True)
             for p, bufs in ce["peers"].items():
-                out[p * n:(p + 1) * n].copy_(bufs[slot], non_blocking=True)         # peer-to-peer read, copy engine
-            out[self.rank * n:(self.rank + 1) * n].copy_(ce["ring"][slot], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(side)
-        out.record_stream(side)
-        ce["ready"][t] = ready
-        return GatherHandle(out, None, y, done)
+                st = ce["push"][p]
+                st.wait_event(base)
+                with torch.cuda.stream(st):
+                    bufs[slot][rows].copy_(y, non_blocking=True)      # peer-to-peer write, copy engine
+                    done_p = torch.cuda.Event()
+                    done_p.record(st)
+                side.wait_event(done_p)
+            ready = dist.all_reduce(ce["flag"], group=self.group, async_op=True)   # "my rows are in every rank's slot"
+        y.record_stream(side)
+        for st in ce["push"].values():
+            y.record_stream(st)
+        ce["ready"] = ready
+        return GatherHandle(ce["ring"][slot], ready, y)
 
     def forward_async(self, x_local: torch.Tensor) -> GatherHandle:
         y = self.model(x_local)
@@ -172,8 +186,9 @@ class ShardedGenerator:
         return GatherHandle(out, work, y)
 
     def forward(self, x_local: torch.Tensor) -> torch.Tensor:
-        """Every rank passes its shard (equal sizes) and receives all outputs, rank-major."""
-        return self.forward_async(x_local).wait()
+        """Every rank passes its shard (equal sizes) and receives all outputs, rank-major (a tensor the caller owns)."""
+        out = self.forward_async(x_local).wait()
+        return out.clone() if self._ce is not None else out
 
     def forward_global(self, x_global: torch.Tensor) -> torch.Tensor:
         """Every rank passes the same global batch (size divisible by the world size)."""
@@ -203,6 +218,8 @@ class ShardedGenerator:
             ev_in = torch.cuda.Event()
             ev_in.record(hs["h2d"])
         cur.wait_event(ev_in)
+        if k >= 2 and hs.get("d2h_done", {}).get(k - 2) is not None:
+            cur.wait_event(hs["d2h_done"].pop(k - 2))    # ring lifetime: the copy-out of step k-2 precedes this step's ready signal
         h = self.forward_async(hs["x"][slot])
         g = h.wait()
         ev_c = torch.cuda.Event()
@@ -212,6 +229,9 @@ class ShardedGenerator:
         with torch.cuda.stream(hs["d2h"]):
             hs["d2h"].wait_event(ev_c)
             out_host_local.copy_(g[self.rank * n:(self.rank + 1) * n], non_blocking=True)
+            ev_o = torch.cuda.Event()
+            ev_o.record(hs["d2h"])
+        hs.setdefault("d2h_done", {})[k] = ev_o
         g.record_stream(hs["d2h"])
         hs["k"] = k + 1
 

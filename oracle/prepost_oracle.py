@@ -30,3 +30,34 @@ def postprocess(y: torch.Tensor, img_u8: np.ndarray, mask_u8: np.ndarray) -> np.
     res = res.to(torch.uint8).permute(0, 2, 3, 1).numpy()                  # :136
     m = mask_u8[..., np.newaxis] // 255                                    # :139
     return img_u8 * m + res * (1 - m)                                      # :140
+
+
+def gaussian_kernel_5x5() -> torch.Tensor:
+    """The 5x5 smoothing kernel of the deployed pipeline (scripts/create_onnx_pipeline.py:66-88, GaussianSmoothing with
+    kernel_size=5, sigma=1.0 as constructed at :127-128).  Note the exponent is -((x - mean) / (2 sigma))^2, as written there."""
+    import math
+    size, std = 5, 1.0
+    grids = torch.meshgrid([torch.arange(size, dtype=torch.float32) for _ in range(2)])
+    kernel = 1
+    mean = (size - 1) / 2
+    for g in grids:
+        kernel = kernel * (1 / (std * math.sqrt(2 * math.pi)) * torch.exp(-((g - mean) / (2 * std)) ** 2))
+    return kernel / torch.sum(kernel)
+
+
+def feather_composite(image_u8: torch.Tensor, mask_u8: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """The blend of the deployed (ONNX) pipeline for a crop already at the model resolution
+    (scripts/create_onnx_pipeline.py:233-245; the bilinear resize to the crop size at :235 is the identity then):
+    image_u8 [N,3,H,W] uint8, mask_u8 [N,1,H,W] uint8 (255 = known), y [N,3,H,W] generator output -> composed uint8 [N,3,H,W].
+    The mask is dilated (3x3 max-pool), smoothed with the 5x5 kernel above on a reflect-padded border and used as the
+    per-pixel blend weight."""
+    import torch.nn.functional as F
+    out = ((y * 0.5 + 0.5) * 255).clamp(0, 255)                                        # :234
+    image = image_u8.to(torch.float32)                                                 # :236
+    mask = mask_u8.to(torch.float32)                                                   # :237
+    mask = F.max_pool2d(mask, 3, stride=1, padding=1)                                  # :238
+    mask = F.pad(mask, (2, 2, 2, 2), mode="reflect")                                   # :117 (GaussianSmoothing.forward)
+    mask = F.conv2d(mask, gaussian_kernel_5x5().view(1, 1, 5, 5), padding="valid")     # :118
+    mask = mask / torch.tensor(255)                                                    # :240
+    composed = image * mask + out * (1 - mask)                                         # :241
+    return composed.clamp(0, 255).to(torch.uint8)                                      # :242

@@ -394,3 +394,40 @@ def test_conv2d_resample_randomized_sweep(emul):
         assert float(np.abs(got - want.numpy()).max()) <= 1e-5 * max(1.0, float(want.abs().max())), cfg
         checked += 1
     assert checked > 150
+
+
+def test_feather_composite_matches_reference_pipeline(emul):
+    """The feathered blend of the deployed pipeline (create_onnx_pipeline.py:233-245): kernel source compiled for the host
+    against (a) the outputs of the reference's own MIGAN_Pipeline.postprocess (tests/golden/feather.npz, written by
+    make_golden_prepost.py in the build container) and (b) the oracle on fresh inputs, including free-form masks."""
+    from migan_b200 import ops, synthetic
+    from oracle import prepost_oracle as P
+    lib = _abi.bind(emul, _abi.PREPOST_SYMBOLS)
+    k = np.ascontiguousarray(ops.feather_kernel().numpy())
+    assert np.array_equal(k, P.gaussian_kernel_5x5().numpy())
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "feather.npz"))
+    for tag in ("a", "b"):
+        image, mask, y = (np.ascontiguousarray(gold[n + "_" + tag]) for n in ("image", "mask", "y"))
+        n, _, H, W = image.shape
+        out = np.empty_like(image)
+        assert lib.b200_feather_composite(_ptr(y), _ptr(image), _ptr(mask), _ptr(out), n, H, W, _ptr(k), None) == 0
+        diff = np.abs(out.astype(np.int32) - gold["out_" + tag].astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (tag, int(diff.max()), float((diff > 0).mean()))
+        known = np.broadcast_to(mask == 255, image.shape)
+        # deep inside the known region the weight is exactly 1: the image must come back unchanged
+    rng = np.random.RandomState(5)
+    H = W = 96
+    image = np.ascontiguousarray(rng.randint(0, 256, size=(2, 3, H, W), dtype=np.uint8))
+    mask = np.stack([synthetic.free_form_mask(H, rng) for _ in range(2)])[:, None] * np.uint8(255)
+    mask = np.ascontiguousarray(mask.astype(np.uint8))
+    y = np.ascontiguousarray((rng.randn(2, 3, H, W) * 0.7).astype(np.float32))
+    out = np.empty_like(image)
+    assert lib.b200_feather_composite(_ptr(y), _ptr(image), _ptr(mask), _ptr(out), 2, H, W, _ptr(k), None) == 0
+    want = P.feather_composite(torch.from_numpy(image), torch.from_numpy(mask), torch.from_numpy(y)).numpy()
+    diff = np.abs(out.astype(np.int32) - want.astype(np.int32))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (int(diff.max()), float((diff > 0).mean()))
+    allk = np.full((1, 1, 32, 32), 255, np.uint8)
+    img1 = np.ascontiguousarray(image[:1, :, :32, :32])
+    out1 = np.empty_like(img1)
+    lib.b200_feather_composite(_ptr(np.ascontiguousarray(y[:1, :, :32, :32])), _ptr(img1), _ptr(allk), _ptr(out1), 1, 32, 32, _ptr(k), None)
+    assert np.array_equal(out1, img1)                       # fully known: weight exactly 1 everywhere

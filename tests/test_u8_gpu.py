@@ -75,3 +75,25 @@ def test_forward_u8_async_serving_loop(cuda_device):
     model.host_wait()
     for i, m, o in zip(imgs, masks, outs):
         assert torch.equal(o, model.forward_u8(i, m))
+
+
+def test_feather_composite_reference_pipeline(cuda_device):
+    """ops.feather_composite == the blend of the deployed pipeline (create_onnx_pipeline.py:233-245): vectors produced by the
+    reference's own MIGAN_Pipeline.postprocess (tests/golden/feather.npz) and the oracle on a 512 x 512 free-form-mask case."""
+    gold = np.load(os.path.join(GOLDEN, "feather.npz"))
+    for tag in ("a", "b"):
+        image, mask, y = (torch.from_numpy(gold[n + "_" + tag]) for n in ("image", "mask", "y"))
+        out = ops.feather_composite(y.to(cuda_device), image.to(cuda_device), mask.to(cuda_device)).cpu()
+        diff = (out.int() - torch.from_numpy(gold["out_" + tag]).int()).abs()
+        assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-3
+    rng = np.random.RandomState(9)
+    R = 512
+    image = torch.from_numpy(rng.randint(0, 256, size=(2, 3, R, R), dtype=np.uint8))
+    mask = torch.from_numpy(np.stack([synthetic.free_form_mask(R, rng) for _ in range(2)])[:, None].astype(np.uint8) * 255)
+    y = torch.from_numpy((rng.randn(2, 3, R, R) * 0.7).astype(np.float32))
+    out = ops.feather_composite(y.to(cuda_device), image.to(cuda_device), mask.to(cuda_device)).cpu()
+    want = P.feather_composite(image, mask, y)
+    diff = (out.int() - want.int()).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-3
+    far = torch.nn.functional.avg_pool2d((mask == 255).float(), 9, stride=1, padding=4) == 1.0     # 4 pixels away from any hole
+    assert torch.equal(out[far.expand_as(out)], image[far.expand_as(image)])
