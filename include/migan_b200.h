@@ -119,6 +119,28 @@ int b200_postprocess_u8(const float* y_nchw, const uint8_t* img_hwc, const uint8
 int b200_feather_composite(const float* y_nchw, const uint8_t* image_nchw, const uint8_t* mask_n1hw, uint8_t* out_nchw,
                            int n, int H, int W, const float* k25_host, void* stream);
 
+/* Arbitrary-resolution crop pipeline of the deployed (ONNX) form, scripts/create_onnx_pipeline.py:121-264 (MIGAN_Pipeline):
+ * the caller's image u8 [3,H,W] and mask u8 [H,W] (255 = known) stay at their own size; the hole's bounding box is padded,
+ * squared and clipped into a crop window, the crop is resized to the model resolution for the generator and the result is
+ * resized back and blended into the image with a feathered mask.  The stages (DEVICE pointers unless noted):
+ *   b200_resize_nearest_u8    mask at another size -> image size (tvF.resize NEAREST, :255)
+ *   b200_hole_flags           flags[x] / flags[W + y] = column x / row y contains a value < 255 (:144-149); copy them to the host
+ *   migan_crop_box            HOST arithmetic of get_masked_bbox (:151-227) -> box = {x_min, x_max, y_min, y_max}
+ *   b200_pipeline_preprocess  crop -> anti-aliased bilinear resize, round -> x[4,res,res] = cat([m/255-0.5, (v*2/255-1)*m/255]) (:229-236)
+ *   b200_pipeline_postprocess y[3,res,res] -> [0,255] -> anti-aliased bilinear resize to the crop -> feathered blend (3x3 max-pool,
+ *                             5x5 smoothing with the 25 HOST taps k25, reflect border) written into image[crop] in place (:238-262)
+ * The resize reproduces what torchvision's tensor `resize` computes on the CPU (ATen's separable anti-aliased filter, fp32
+ * fused multiply-adds, width pass first) bit for bit; a pass whose size does not change is the identity.
+ * scratch: b200_pipeline_scratch_bytes(H, W, res) bytes of device memory, shared by the two stages. */
+size_t b200_pipeline_scratch_bytes(int H, int W, int res);
+int b200_resize_nearest_u8(const uint8_t* in_hw, int H, int W, uint8_t* out_hw, int out_h, int out_w, void* stream);
+int b200_hole_flags(const uint8_t* mask_hw, int H, int W, uint8_t* flags_w_plus_h, void* stream);
+int migan_crop_box(const uint8_t* flags_host, int H, int W, int resolution, int padding, int* box4_host);
+int b200_pipeline_preprocess(const uint8_t* image_chw, const uint8_t* mask_hw, int H, int W, const int* box4_host, int resolution,
+                             float* x_nchw, void* scratch, size_t scratch_bytes, void* stream);
+int b200_pipeline_postprocess(const float* y_nchw, uint8_t* image_chw, const uint8_t* mask_hw, int H, int W, const int* box4_host,
+                              int resolution, const float* k25_host, void* scratch, size_t scratch_bytes, void* stream);
+
 /* Kernels launched by the most recent migan_forward on this context. */
 int migan_last_launch_count(const migan_ctx* ctx);
 

@@ -71,4 +71,15 @@ int launch_preprocess_u8(const uint8_t* img_hwc, const uint8_t* mask_hw, float* 
 int launch_postprocess_u8(const float* y_nchw, const uint8_t* img_hwc, const uint8_t* mask_hw, uint8_t* out_hwc, int n, int r,
                           cudaStream_t s);
 
+
+// ---- arbitrary-resolution crop pipeline (pipeline.cu): scripts/create_onnx_pipeline.py:121-264 ------
+size_t pipeline_scratch_bytes(int H, int W, int res);
+int launch_resize_nearest_u8(const uint8_t* in, int H, int W, uint8_t* out, int oh, int ow, cudaStream_t s);
+int launch_hole_flags(const uint8_t* mask, int H, int W, uint8_t* flags, cudaStream_t s);
+void crop_box_from_flags(const uint8_t* flags_host, int H, int W, int res, int padding, int* box4);
+int launch_pipeline_preprocess(const uint8_t* image, const uint8_t* mask, int H, int W, const int* box, int res, float* x,
+                               void* scratch, cudaStream_t s);
+int launch_pipeline_postprocess(const float* y, uint8_t* image, const uint8_t* mask, int H, int W, const int* box, int res,
+                                const float* k25_host, void* scratch, cudaStream_t s);
+
 }  // namespace migan

@@ -1225,6 +1225,63 @@ int b200_feather_composite(const float* y, const uint8_t* img, const uint8_t* ma
     return MIGAN_OK;
 }
 
+// ---- arbitrary-resolution crop pipeline (scripts/create_onnx_pipeline.py:121-264), kernels in pipeline.cu ----
+size_t b200_pipeline_scratch_bytes(int H, int W, int res) {
+    if (H < 1 || W < 1 || res < 1) return 0;
+    return migan::pipeline_scratch_bytes(H, W, res);
+}
+
+int b200_resize_nearest_u8(const uint8_t* in, int H, int W, uint8_t* out, int oh, int ow, void* stream) {
+    if (!in || !out) return fail(MIGAN_ERR_INVALID, "resize_nearest_u8: null argument");
+    if (H < 1 || W < 1 || oh < 1 || ow < 1) return fail(MIGAN_ERR_INVALID, "resize_nearest_u8: bad size %d x %d -> %d x %d", H, W, oh, ow);
+    CUDA_TRY((cudaError_t)migan::launch_resize_nearest_u8(in, H, W, out, oh, ow, static_cast<cudaStream_t>(stream)));
+    return MIGAN_OK;
+}
+
+int b200_hole_flags(const uint8_t* mask, int H, int W, uint8_t* flags, void* stream) {
+    if (!mask || !flags) return fail(MIGAN_ERR_INVALID, "hole_flags: null argument");
+    if (H < 1 || W < 1) return fail(MIGAN_ERR_INVALID, "hole_flags: bad size %d x %d", H, W);
+    CUDA_TRY((cudaError_t)migan::launch_hole_flags(mask, H, W, flags, static_cast<cudaStream_t>(stream)));
+    return MIGAN_OK;
+}
+
+int migan_crop_box(const uint8_t* flags_host, int H, int W, int res, int padding, int* box4) {
+    if (!flags_host || !box4) return fail(MIGAN_ERR_INVALID, "crop_box: null argument");
+    if (H < 1 || W < 1 || res < 1 || padding < 0) return fail(MIGAN_ERR_INVALID, "crop_box: bad arguments (%d x %d, resolution %d, padding %d)", H, W, res, padding);
+    migan::crop_box_from_flags(flags_host, H, W, res, padding, box4);
+    return MIGAN_OK;
+}
+
+static int check_box(const char* who, int H, int W, const int* box) {
+    if (!box) return fail(MIGAN_ERR_INVALID, "%s: null crop window", who);
+    if (box[0] < 0 || box[1] > W || box[2] < 0 || box[3] > H || box[1] - box[0] < 3 || box[3] - box[2] < 3)
+        return fail(MIGAN_ERR_INVALID, "%s: crop window x[%d,%d) y[%d,%d) must lie inside the %d x %d image and be at least 3 x 3",
+                    who, box[0], box[1], box[2], box[3], H, W);
+    return MIGAN_OK;
+}
+
+int b200_pipeline_preprocess(const uint8_t* image, const uint8_t* mask, int H, int W, const int* box, int res, float* x,
+                             void* scratch, size_t scratch_bytes, void* stream) {
+    if (!image || !mask || !x || !scratch) return fail(MIGAN_ERR_INVALID, "pipeline_preprocess: null argument");
+    if (int rc = check_box("pipeline_preprocess", H, W, box)) return rc;
+    if (res < 1) return fail(MIGAN_ERR_INVALID, "pipeline_preprocess: bad resolution %d", res);
+    if (scratch_bytes < migan::pipeline_scratch_bytes(H, W, res))
+        return fail(MIGAN_ERR_WORKSPACE, "pipeline_preprocess: scratch of %zu bytes, need %zu", scratch_bytes, migan::pipeline_scratch_bytes(H, W, res));
+    CUDA_TRY((cudaError_t)migan::launch_pipeline_preprocess(image, mask, H, W, box, res, x, scratch, static_cast<cudaStream_t>(stream)));
+    return MIGAN_OK;
+}
+
+int b200_pipeline_postprocess(const float* y, uint8_t* image, const uint8_t* mask, int H, int W, const int* box, int res,
+                              const float* k25, void* scratch, size_t scratch_bytes, void* stream) {
+    if (!y || !image || !mask || !k25 || !scratch) return fail(MIGAN_ERR_INVALID, "pipeline_postprocess: null argument");
+    if (int rc = check_box("pipeline_postprocess", H, W, box)) return rc;
+    if (res < 1) return fail(MIGAN_ERR_INVALID, "pipeline_postprocess: bad resolution %d", res);
+    if (scratch_bytes < migan::pipeline_scratch_bytes(H, W, res))
+        return fail(MIGAN_ERR_WORKSPACE, "pipeline_postprocess: scratch of %zu bytes, need %zu", scratch_bytes, migan::pipeline_scratch_bytes(H, W, res));
+    CUDA_TRY((cudaError_t)migan::launch_pipeline_postprocess(y, image, mask, H, W, box, res, k25, scratch, static_cast<cudaStream_t>(stream)));
+    return MIGAN_OK;
+}
+
 int migan_host_wait(migan_ctx* ctx) {
     if (!ctx) return fail(MIGAN_ERR_INVALID, "null ctx");
     if (!ctx->s_out) return MIGAN_OK;

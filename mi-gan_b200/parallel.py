@@ -149,7 +149,9 @@ class ShardedGenerator:
             base = torch.cuda.Event()
             base.record(side)
             ce["ring"][slot][rows].copy_(y, non_blocking=True)
-            for p, bufs in ce["peers"].items():
+            for k in range(1, self.world_size):       # staggered: at step k every rank writes to a different destination
+                p = (self.rank + k) % self.world_size
+                bufs = ce["peers"][p]
                 st = ce["push"][p]
                 st.wait_event(base)
                 with torch.cuda.stream(st):

@@ -15,11 +15,14 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 51 -c 51 --csv --lo
 # ... and full captures per kernel class, second forward, 32 images
 timeout 500 $NCU -k regex:sepconv_tc -s 32 -c 5 -f -o gpurun_out/r02_ncu_tc_enc python tools/ncu_target.py > gpurun_out/ncu_a.log 2>&1
 timeout 600 $NCU -k regex:sepconv_tc -s 56 -c 8 -f -o gpurun_out/r02_ncu_tc_syn python tools/ncu_target.py > gpurun_out/ncu_b.log 2>&1
-timeout 400 $NCU -k regex:"dw3x3_down|torgb_img|dw3x3_act|up2_noise" -s 16 -c 8 -f -o gpurun_out/r02_ncu_ew python tools/ncu_target.py > gpurun_out/ncu_c.log 2>&1
+timeout 400 $NCU -k regex:"dw3x3_down|torgb_img|dw3x3_act|up2_noise" -s 18 -c 18 -f -o gpurun_out/r02_ncu_ew python tools/ncu_target.py > gpurun_out/ncu_c.log 2>&1
 for f in r02_ncu_tc_enc r02_ncu_tc_syn r02_ncu_ew; do
   ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/$f.raw.csv 2>/dev/null
   ncu -i gpurun_out/$f.ncu-rep --page source --csv > gpurun_out/$f.source.csv 2>/dev/null
 done
+# the reports and source pages (~120 MB) do not fit gpurun's 64 MiB return channel: summarise the source view here, keep the raw pages
+python tools/summarize_profiles.py --lines-only
+rm -f gpurun_out/*.ncu-rep gpurun_out/*.source.csv
 # Co-Mod-GAN: exact fp32 path (default) and the tcgen05 route
 timeout 300 python bench.py --workload comodgan --steps 5 --warmup 3 > gpurun_out/r02_bench_comodgan256_bs16.json 2> gpurun_out/r02_bench_comod.err
 timeout 200 python bench.py --workload comodgan --comod-gemm tc --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_comodgan256_bs16_tc.json 2>> gpurun_out/r02_bench_comod.err

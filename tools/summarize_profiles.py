@@ -60,7 +60,24 @@ def table(name):
     return "\n".join(out), recs
 
 
+def lines_only():
+    """On the GPU box: per-source-line instruction / stall attribution of the two heaviest launches -> gpurun_out/r02_ncu_lines_*.txt."""
+    dis = os.path.join(SRC, "cub_final", "tc.dis")
+    os.makedirs(os.path.dirname(dis), exist_ok=True)
+    lib = os.path.join(ROOT, "mi-gan_b200", "lib", "libmigan_b200.so")
+    subprocess.run("cd %s && cuobjdump -xelf all %s > /dev/null 2>&1 && nvdisasm -g -c sepconv_tc.sm_100a.cubin > tc.dis" % (os.path.dirname(dis), lib), shell=True)
+    for name, idx, tag in (("r02_ncu_tc_enc", 0, "enc_b512_conv1_stem"), ("r02_ncu_tc_enc", 2, "enc_b256_conv1_nhwc"),
+                           ("r02_ncu_tc_syn", 7, "syn_b512_conv2_up_torgb")):
+        src = os.path.join(SRC, name + ".source.csv")
+        if os.path.exists(src) and os.path.exists(dis):
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), src, dis, str(idx), "40"], capture_output=True, text=True).stdout
+            open(os.path.join(SRC, "r02_ncu_lines_%s.txt" % tag), "w").write(out)
+    shutil.rmtree(os.path.dirname(dis), ignore_errors=True)
+
+
 def main():
+    if "--lines-only" in sys.argv:
+        return lines_only()
     os.makedirs(DST, exist_ok=True)
     for f in COPY:
         p = os.path.join(SRC, f)
@@ -91,17 +108,11 @@ def main():
     open(os.path.join(DST, "r02_ncu_summary.md"), "w").write("\n".join(parts) + "\n")
     if traffic:
         json.dump(traffic, open(os.path.join(DST, "traffic.json"), "w"), indent=1)
-    # per-source-line attribution of the two heaviest launches
-    dis = os.path.join(SRC, "cub_final", "tc.dis")
-    if not os.path.exists(dis):
-        os.makedirs(os.path.dirname(dis), exist_ok=True)
-        lib = os.path.join(ROOT, "mi-gan_b200", "lib", "libmigan_b200.so")
-        subprocess.run("cd %s && cuobjdump -xelf all %s > /dev/null 2>&1 && nvdisasm -g -c sepconv_tc.sm_100a.cubin > tc.dis" % (os.path.dirname(dis), lib), shell=True)
-    for name, idx, tag in (("r02_ncu_tc_enc", 0, "enc_b512_conv1_stem"), ("r02_ncu_tc_syn", 7, "syn_b512_conv2_up_torgb")):
-        src = os.path.join(SRC, name + ".source.csv")
-        if os.path.exists(src) and os.path.exists(dis):
-            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), src, dis, str(idx), "30"], capture_output=True, text=True).stdout
-            open(os.path.join(DST, "r02_ncu_lines_%s.txt" % tag), "w").write(out)
+    # per-source-line attribution of the two heaviest launches: made on the GPU box (--lines-only, the source pages are too
+    # large to travel), copied here
+    for f in sorted(os.listdir(SRC)):
+        if f.startswith("r02_ncu_lines_"):
+            shutil.copy(os.path.join(SRC, f), os.path.join(DST, f))
     print("profiles/ updated")
 
 
