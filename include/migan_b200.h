@@ -141,6 +141,13 @@ int b200_pipeline_preprocess(const uint8_t* image_chw, const uint8_t* mask_hw, i
 int b200_pipeline_postprocess(const float* y_nchw, uint8_t* image_chw, const uint8_t* mask_hw, int H, int W, const int* box4_host,
                               int resolution, const float* k25_host, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Stream memory operations for multi-GPU signalling (mi-gan_b200/parallel.py): the stream waits until the 32-bit word at a
+ * DEVICE address reaches `value` (cyclic comparison (int32)(*addr - value) >= 0), or writes `value` to it, in stream order.
+ * Executed by the stream's front end: no kernel, no SM.  b200_stream_memops_available() is 1 when the driver offers them. */
+int b200_stream_memops_available(void);
+int b200_stream_wait_value32(void* stream, void* addr, uint32_t value);
+int b200_stream_write_value32(void* stream, void* addr, uint32_t value);
+
 /* Kernels launched by the most recent migan_forward on this context. */
 int migan_last_launch_count(const migan_ctx* ctx);
 

@@ -1225,6 +1225,40 @@ int b200_feather_composite(const float* y, const uint8_t* img, const uint8_t* ma
     return MIGAN_OK;
 }
 
+// ---- stream memory operations (multi-GPU signalling without a kernel) ----------------------------------------------------
+// cuStreamWaitValue32 / cuStreamWriteValue32 through the runtime's driver entry points (the library has no libcuda link
+// dependency).  A wait is executed by the stream's front end: no SM is occupied while a rank waits for its peers.
+typedef int (*StreamMemOp32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static StreamMemOp32Fn stream_memop(const char* name) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<StreamMemOp32Fn>(ptr);
+}
+
+int b200_stream_memops_available(void) {
+    static const int ok = (stream_memop("cuStreamWaitValue32") && stream_memop("cuStreamWriteValue32")) ? 1 : 0;
+    return ok;
+}
+
+int b200_stream_wait_value32(void* stream, void* addr, uint32_t value) {
+    static const StreamMemOp32Fn fn = stream_memop("cuStreamWaitValue32");
+    if (!fn) return fail(MIGAN_ERR_CUDA, "cuStreamWaitValue32 entry point not available");
+    if (!addr) return fail(MIGAN_ERR_INVALID, "stream_wait_value32: null address");
+    const int r = fn(static_cast<cudaStream_t>(stream), (unsigned long long)(uintptr_t)addr, value, 0u /* CU_STREAM_WAIT_VALUE_GEQ: (int32)(*addr - value) >= 0 */);
+    if (r != 0) return fail(MIGAN_ERR_CUDA, "cuStreamWaitValue32 failed with CUresult %d", r);
+    return MIGAN_OK;
+}
+
+int b200_stream_write_value32(void* stream, void* addr, uint32_t value) {
+    static const StreamMemOp32Fn fn = stream_memop("cuStreamWriteValue32");
+    if (!fn) return fail(MIGAN_ERR_CUDA, "cuStreamWriteValue32 entry point not available");
+    if (!addr) return fail(MIGAN_ERR_INVALID, "stream_write_value32: null address");
+    const int r = fn(static_cast<cudaStream_t>(stream), (unsigned long long)(uintptr_t)addr, value, 0u);
+    if (r != 0) return fail(MIGAN_ERR_CUDA, "cuStreamWriteValue32 failed with CUresult %d", r);
+    return MIGAN_OK;
+}
+
 // ---- arbitrary-resolution crop pipeline (scripts/create_onnx_pipeline.py:121-264), kernels in pipeline.cu ----
 size_t b200_pipeline_scratch_bytes(int H, int W, int res) {
     if (H < 1 || W < 1 || res < 1) return 0;

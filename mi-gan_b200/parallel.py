@@ -21,9 +21,9 @@ import torch.distributed as dist
 def configure_overlap(reserve_sms: int = None, nccl_channels: int = 8, gather: str = "ce") -> None:
     """Call BEFORE `init_process_group` and before the first forward.
 
-    gather = "ce" (default): the output all-gather moves its bytes with the copy engines (peer-to-peer reads over NVLink, see
-    `ShardedGenerator`); the only NCCL kernel per step is an 8-byte all-reduce used as the ready signal, so the persistent
-    tensor-core kernel keeps all 148 SMs (no reservation).
+    gather = "ce" (default): the output all-gather moves its bytes with the copy engines (peer-to-peer writes over NVLink, see
+    `ShardedGenerator`) and signals completion with stream memory operations (or, MIGAN_CE_SIGNAL=nccl, an 8-byte all-reduce):
+    no collective kernel runs, the persistent tensor-core kernel keeps all 148 SMs (no reservation).
     gather = "nccl": `all_gather_into_tensor` runs on NCCL's SM-resident copy kernels, one SM per channel, concurrently with
     the next batch's kernels.  The persistent kernel uses one CTA per SM -- if they collide, its last CTAs run as a second
     wave -- so NCCL is limited to `nccl_channels` channels and the persistent grids leave `reserve_sms` SMs free.  Measured
@@ -77,6 +77,12 @@ class ShardedGenerator:
       collective, and the transfer of batch t overlaps the compute of batch t+1.  LIFETIME: `forward_async` returns a view of
       the ring; it stays valid until RING - 1 further `forward_async` calls (consume or clone it before).  `forward` /
       `forward_global` return a private copy.
+      Ready signal (`signal`, env MIGAN_CE_SIGNAL): "memops" (default when the driver offers stream memory operations) --
+      after its rows the sender copies a 4-byte step counter into the receiver's arrival table, and the receiver's stream
+      waits on those words with `cuStreamWaitValue32`; no kernel runs for the collective at all, so the persistent
+      tensor-core kernel (one CTA per SM, static tile assignment) never finds an SM taken by a spinning collective kernel.
+      "nccl": the 8-byte all-reduce described above (measured on 8 B200s: its kernel, waiting for the slowest rank while
+      holding an SM, made the compute kernels' last CTAs run as a second wave: 0.65 scaling efficiency).
     gather = "auto": "ce" when possible, else "nccl"."""
 
     RING = 4   # gathered buffers per rank (copy-engine path): the tensor of step t is valid until forward_async(t + RING - 1)
@@ -128,6 +134,26 @@ class ShardedGenerator:
         self._ce = {"ring": ring, "peers": peers, "side": torch.cuda.Stream(device=y.device),
                     "push": {p: torch.cuda.Stream(device=y.device) for p in peers},
                     "flag": torch.zeros(1, device=y.device), "ready": None, "shape": tuple(y.shape)}
+        signal = os.environ.get("MIGAN_CE_SIGNAL", "memops")
+        if signal == "memops":
+            from . import _abi
+            if not _abi.load().b200_stream_memops_available():
+                signal = "nccl"
+        votes = [None] * self.world_size
+        dist.all_gather_object(votes, signal, group=self.group)
+        signal = "memops" if all(v == "memops" for v in votes) else "nccl"      # every rank must use the same protocol
+        self._ce["signal"] = signal
+        if signal == "memops":
+            # arrival table: arrive[q] = (last step + 1) whose rows from rank q have landed in this rank's ring
+            arrive = torch.zeros(self.world_size, dtype=torch.int32, device=y.device)
+            stage = torch.zeros(self.world_size, dtype=torch.int32, device=y.device)    # per-destination source word of the 4-byte copy
+            tables = [None] * self.world_size
+            dist.all_gather_object(tables, reduce_tensor(arrive), group=self.group)
+            self._ce["arrive"] = arrive
+            self._ce["stage"] = stage
+            self._ce["peer_arrive"] = {p: tables[p][0](*tables[p][1]) for p in peers}
+            torch.cuda.synchronize(y.device)
+            dist.barrier(group=self.group)              # every table is zeroed and mapped before the first signal is sent
 
     def _forward_ce(self, y: torch.Tensor) -> GatherHandle:
         """Push form: this rank writes its rows into slot t % RING of EVERY rank's gathered ring (posted peer-to-peer writes,
@@ -136,6 +162,8 @@ class ShardedGenerator:
         by the lifetime rule of `forward_async`, is no longer in use once its owner has CALLED forward_async(t - 1) -- which is
         what the completed ready signal of step t - 1 certifies for every rank."""
         ce, t, n = self._ce, self._step, y.shape[0]
+        if ce["signal"] == "memops":
+            return self._forward_ce_memops(y)
         slot = t % self.RING
         cur = torch.cuda.current_stream(y.device)
         ev = torch.cuda.Event()
@@ -165,6 +193,46 @@ class ShardedGenerator:
             y.record_stream(st)
         ce["ready"] = ready
         return GatherHandle(ce["ring"][slot], ready, y)
+
+    def _forward_ce_memops(self, y: torch.Tensor) -> GatherHandle:
+        """Push form with no collective kernel.  Per destination q, on its own stream: wait until q's rows of step t-1 have
+        landed HERE (arrive[q] >= t: q has then passed its forward_async(t-1), i.e. is done with the slot about to be
+        overwritten -- the lifetime rule of `forward_async`), copy this rank's rows into slot t % RING of q's ring, then copy
+        the step counter t+1 into q's arrival table.  The gathered tensor is complete here when arrive[q] >= t+1 for every q;
+        those waits run on a side stream, the consumer waits for one event."""
+        from . import _abi
+        lib = _abi.load()
+        ce, t, n = self._ce, self._step, y.shape[0]
+        slot = t % self.RING
+        cur = torch.cuda.current_stream(y.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        side = ce["side"]
+        rows = slice(self.rank * n, (self.rank + 1) * n)
+        arrive, stage = ce["arrive"], ce["stage"]
+        word = arrive.element_size()
+        tv, tn = t & 0xFFFFFFFF, (t + 1) & 0xFFFFFFFF
+        with torch.cuda.device(y.device):
+            for k in range(1, self.world_size):       # staggered: at step k every rank writes to a different destination
+                p = (self.rank + k) % self.world_size
+                st = ce["push"][p]
+                st.wait_event(ev)
+                _abi.check(lib.b200_stream_wait_value32(st.cuda_stream, arrive.data_ptr() + p * word, tv))
+                with torch.cuda.stream(st):
+                    ce["peers"][p][slot][rows].copy_(y, non_blocking=True)                       # peer-to-peer write, copy engine
+                _abi.check(lib.b200_stream_write_value32(st.cuda_stream, stage.data_ptr() + p * word, tn))
+                with torch.cuda.stream(st):
+                    ce["peer_arrive"][p][self.rank:self.rank + 1].copy_(stage[p:p + 1], non_blocking=True)   # 4 bytes: "my rows of step t are in"
+                y.record_stream(st)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                ce["ring"][slot][rows].copy_(y, non_blocking=True)
+                for p in ce["peers"]:
+                    _abi.check(lib.b200_stream_wait_value32(side.cuda_stream, arrive.data_ptr() + p * word, tn))
+                done = torch.cuda.Event()
+                done.record(side)
+            y.record_stream(side)
+        return GatherHandle(ce["ring"][slot], None, y, done)
 
     def forward_async(self, x_local: torch.Tensor) -> GatherHandle:
         y = self.model(x_local)
@@ -244,6 +312,7 @@ class ShardedGenerator:
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
             self._ce["peers"].clear()
+            self._ce.get("peer_arrive", {}).clear()
             dist.barrier(group=self.group)
             self._ce = None
 
