@@ -48,8 +48,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true",
                     help="N > 1: skip the output all-gather (shows what the collective costs; not the north_star configuration)")
-    ap.add_argument("--gather", default="ce", choices=["ce", "nccl"],
-                    help="N > 1: output all-gather by copy-engine peer writes + a stream-memory-operation ready signal (default; MIGAN_CE_SIGNAL=nccl: 8-byte all-reduce), or NCCL all_gather_into_tensor")
+    ap.add_argument("--gather", default="auto", choices=["auto", "ce", "nccl"],
+                    help="N > 1: output all-gather by copy-engine peer reads + an 8-byte NCCL ready signal (ce), NCCL all_gather_into_tensor "
+                         "with 8 SMs left free for its 8 channels (nccl), or whichever measured faster at this world size (auto: ce at 2 GPUs, nccl above)")
     ap.add_argument("--masks", default="free_form", choices=["free_form", "blocks"], help="synthetic hole masks")
     ap.add_argument("--profile-out", default=None, help="write the per-launch table (JSON) here")
     args = ap.parse_args()
@@ -421,7 +422,7 @@ def run_b200(args):
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.path != "tc_fast" else "f16",
         "data": "synthetic",
-        "config": {"workload": "migan-%d Generator.forward, %d images/GPU%s" % (R, B, (", all-gather of outputs (%s)" % (("copy-engine peer writes over NVLink, ready signal: %s" % (sharded._ce or {}).get("signal", "?")) if args.gather == "ce" else "NCCL all_gather_into_tensor")) if sharded is not None else (", no gather" if world > 1 else "")),
+        "config": {"workload": "migan-%d Generator.forward, %d images/GPU%s" % (R, B, (", all-gather of outputs (%s)" % ("copy-engine peer reads over NVLink + 8-byte NCCL ready signal" if sharded.gather == "ce" else "NCCL all_gather_into_tensor, %s channels, %s SMs left free for them" % (os.environ.get("NCCL_MAX_NCHANNELS", "?"), os.environ.get("MIGAN_TC_RESERVE_SMS", "0")))) if sharded is not None else (", no gather" if world > 1 else "")),
                    "masks": "free-form (rectangles + brush strokes, evaluate_fid_lpips.py protocol)" if args.masks == "free_form" else "8x8-cell blocks",
                    "path": args.path, "arithmetic": "fp32 CUDA-core depthwise/FIR; 1x1 convs on tcgen05 as fp16 hi/lo 3-pass split with fp32 accumulate"
                    if args.path == "tc" else args.path,

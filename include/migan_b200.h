@@ -147,6 +147,12 @@ int b200_pipeline_postprocess(const float* y_nchw, uint8_t* image_chw, const uin
 int b200_stream_memops_available(void);
 int b200_stream_wait_value32(void* stream, void* addr, uint32_t value);
 int b200_stream_write_value32(void* stream, void* addr, uint32_t value);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): one copy-engine transfer between any two mapped device
+ * addresses (local or a peer's), enqueued on `stream` of the CURRENT device and nothing else (no cross-device event exchange). */
+int b200_memcpy_async(void* dst, const void* src, size_t bytes, void* stream);
+/* cudaDeviceEnablePeerAccess(peer_device) for the CURRENT device (already enabled is not an error): copies between the two
+ * devices' memory then go directly over NVLink instead of being staged. */
+int b200_enable_peer_access(int peer_device);
 
 /* Kernels launched by the most recent migan_forward on this context. */
 int migan_last_launch_count(const migan_ctx* ctx);

@@ -45,6 +45,8 @@ SYMBOLS = [
     ("b200_stream_memops_available", c_int, []),
     ("b200_stream_wait_value32", c_int, [c_void_p, c_void_p, ctypes.c_uint32]),
     ("b200_stream_write_value32", c_int, [c_void_p, c_void_p, ctypes.c_uint32]),
+    ("b200_memcpy_async", c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    ("b200_enable_peer_access", c_int, [c_int]),
     ("migan_last_launch_count", c_int, [c_void_p]),
     ("migan_set_profiling", c_int, [c_void_p, c_int]),
     ("migan_profile_num_steps", c_int, [c_void_p]),

@@ -1259,6 +1259,19 @@ int b200_stream_write_value32(void* stream, void* addr, uint32_t value) {
     return MIGAN_OK;
 }
 
+int b200_enable_peer_access(int peer_device) {
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return MIGAN_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(MIGAN_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e)); }
+    return MIGAN_OK;
+}
+
+int b200_memcpy_async(void* dst, const void* src, size_t bytes, void* stream) {
+    if (!dst || !src) return fail(MIGAN_ERR_INVALID, "memcpy_async: null argument");
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+    return MIGAN_OK;
+}
+
 // ---- arbitrary-resolution crop pipeline (scripts/create_onnx_pipeline.py:121-264), kernels in pipeline.cu ----
 size_t b200_pipeline_scratch_bytes(int H, int W, int res) {
     if (H < 1 || W < 1 || res < 1) return 0;

@@ -18,18 +18,31 @@ import torch
 import torch.distributed as dist
 
 
-def configure_overlap(reserve_sms: int = None, nccl_channels: int = 8, gather: str = "ce") -> None:
+def resolve_gather(gather: str, world_size: int) -> str:
+    """'auto' -> the implementation that measured best at this world size on B200s (round 2, migan-512, 32 images per GPU):
+    2 GPUs: copy engines 10.23 ms/step vs NCCL all-gather 10.52 (one GPU 9.97);  8 GPUs: NCCL all-gather 11.90 ms/step vs copy
+    engines 13.8-14.9 (one GPU 9.70).  4 GPUs were not measured and take the NCCL path."""
+    if gather != "auto":
+        return gather
+    return "ce" if world_size == 2 else "nccl"
+
+
+def configure_overlap(reserve_sms: int = None, nccl_channels: int = 8, gather: str = "auto", world_size: int = None) -> None:
     """Call BEFORE `init_process_group` and before the first forward.
 
-    gather = "ce" (default): the output all-gather moves its bytes with the copy engines (peer-to-peer writes over NVLink, see
-    `ShardedGenerator`) and signals completion with stream memory operations (or, MIGAN_CE_SIGNAL=nccl, an 8-byte all-reduce):
-    no collective kernel runs, the persistent tensor-core kernel keeps all 148 SMs (no reservation).
+    gather = "ce": the output all-gather moves its bytes with the copy engines (peer-to-peer reads over NVLink, see
+    `ShardedGenerator`); the only NCCL kernel per step is an 8-byte all-reduce used as the ready signal, so the persistent
+    tensor-core kernel keeps all 148 SMs (no reservation).
     gather = "nccl": `all_gather_into_tensor` runs on NCCL's SM-resident copy kernels, one SM per channel, concurrently with
     the next batch's kernels.  The persistent kernel uses one CTA per SM -- if they collide, its last CTAs run as a second
     wave -- so NCCL is limited to `nccl_channels` channels and the persistent grids leave `reserve_sms` SMs free.  Measured
     on 2 B200s (migan-512, 32 img/GPU, round 1): 14.27 ms/step without the reservation, 13.3-13.4 ms with 4-8 SMs reserved
-    (12.9 ms on one GPU).  Respects values already present in the environment."""
-    if gather == "nccl":
+    (12.9 ms on one GPU).
+    gather = "auto" (default): see `resolve_gather`; `world_size` defaults to the WORLD_SIZE of the launcher.
+    Respects values already present in the environment."""
+    if world_size is None:
+        world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if resolve_gather(gather, world_size) == "nccl":
         os.environ.setdefault("NCCL_MAX_NCHANNELS", str(nccl_channels))
         os.environ.setdefault("NCCL_MIN_NCHANNELS", str(nccl_channels))
         os.environ.setdefault("MIGAN_TC_RESERVE_SMS", str(8 if reserve_sms is None else reserve_sms))
@@ -70,22 +83,21 @@ class ShardedGenerator:
 
     gather = "nccl": one `all_gather_into_tensor` per batch (NCCL's copy kernels, SM-resident).
     gather = "ce" (CUDA tensors, all ranks on one box): the same all-gather with the bytes moved by the copy engines.  Every
-      rank publishes a ring of RING gathered-output buffers to its peers once (CUDA IPC, through torch's tensor sharing); per
-      batch it (1) writes its rows into the current slot of every rank's ring with peer-to-peer `cudaMemcpyAsync` over NVLink
-      (one stream per peer), then (2) joins an 8-byte NCCL all-reduce -- the only collective kernel -- whose completion means
-      "every rank's rows have landed here".  No SM is taken from the compute kernels, so nothing has to be reserved for the
-      collective, and the transfer of batch t overlaps the compute of batch t+1.  LIFETIME: `forward_async` returns a view of
-      the ring; it stays valid until RING - 1 further `forward_async` calls (consume or clone it before).  `forward` /
-      `forward_global` return a private copy.
-      Ready signal (`signal`, env MIGAN_CE_SIGNAL): "memops" (default when the driver offers stream memory operations) --
-      after its rows the sender copies a 4-byte step counter into the receiver's arrival table, and the receiver's stream
-      waits on those words with `cuStreamWaitValue32`; no kernel runs for the collective at all, so the persistent
-      tensor-core kernel (one CTA per SM, static tile assignment) never finds an SM taken by a spinning collective kernel.
-      "nccl": the 8-byte all-reduce described above (measured on 8 B200s: its kernel, waiting for the slowest rank while
-      holding an SM, made the compute kernels' last CTAs run as a second wave: 0.65 scaling efficiency).
-    gather = "auto": "ce" when possible, else "nccl"."""
+      rank publishes a small ring of output buffers to its peers once (CUDA IPC, through torch's tensor sharing); per batch
+      it (1) puts its y into the ring, (2) joins an 8-byte NCCL all-reduce -- the only collective kernel, used as the "every
+      rank's y is in place" signal -- and (3) pulls the 7 peer shards into a fresh gathered tensor with peer-to-peer
+      `cudaMemcpyAsync` reads over NVLink on a side stream.  No SM is taken from the compute kernels, so nothing has to be
+      reserved for the collective, and the pull of batch t overlaps the compute of batch t+1.
+      Measured (round 2): 2 B200s 10.23 ms/step = 0.975 of 2 x one GPU; 8 B200s 13.8-14.9 ms/step -- there the NCCL path is
+      faster (11.9).  Variants tried on hardware and dropped: the same pull with a staggered source order and 2 SMs left
+      free for the signal's kernel (13.8 ms at 8 GPUs); a push form with bare `cudaMemcpyAsync` on the sender's own
+      streams (10.26 ms at 2 GPUs, 41 ms at 8); signalling with `cuStreamWaitValue32` and 4-byte peer writes instead of
+      the all-reduce (no collective kernel; bit-exact but 11.3 ms at 2 GPUs: a stream parked in a memory wait delays the
+      streams sharing its hardware queue).  `tools/p2p_probe.py` holds the primitive measurements (peer copy 475-550 GB/s,
+      signal latency 8 us, no slow-down of a concurrent forward).
+    gather = "auto" (default): `resolve_gather` -- "ce" at 2 GPUs, "nccl" above."""
 
-    RING = 4   # gathered buffers per rank (copy-engine path): the tensor of step t is valid until forward_async(t + RING - 1)
+    RING = 3   # published y buffers per rank: slot t % RING is rewritten only after the ready signal of step t - RING + 1
 
     def __init__(self, model: Callable[[torch.Tensor], torch.Tensor], group: Optional[dist.ProcessGroup] = None,
                  gather: str = "auto"):
@@ -97,7 +109,8 @@ class ShardedGenerator:
         self.group = group
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.gather = gather
+        self.gather = resolve_gather(gather, self.world_size) if gather == "auto" else gather
+        self._fallback_ok = (gather == "auto")     # "auto" may fall back to NCCL when the peers cannot map each other's memory
         self._ce = None          # lazily built state of the copy-engine path
         self._step = 0
 
@@ -118,10 +131,9 @@ class ShardedGenerator:
 
     # -- copy-engine all-gather ---------------------------------------------------------------------------------------
     def _setup_ce(self, y: torch.Tensor):
-        """Publish RING gathered-output buffers to every peer and map theirs (one-time, collective)."""
+        """Publish RING output buffers of y's shape to every peer and map theirs (one-time, collective)."""
         from torch.multiprocessing.reductions import reduce_tensor
-        n = y.shape[0]
-        ring = [torch.empty((self.world_size * n,) + tuple(y.shape[1:]), dtype=y.dtype, device=y.device) for _ in range(self.RING)]
+        ring = [torch.empty_like(y) for _ in range(self.RING)]
         mine = [reduce_tensor(t) for t in ring]                       # (rebuild_fn, args): CUDA IPC handle + offset
         everyone = [None] * self.world_size
         dist.all_gather_object(everyone, mine, group=self.group)
@@ -129,122 +141,47 @@ class ShardedGenerator:
         for p in range(self.world_size):
             if p != self.rank:
                 peers[p] = [fn(*args) for fn, args in everyone[p]]    # tensors aliasing rank p's ring (peer-mapped)
-                if tuple(peers[p][0].shape) != tuple(ring[0].shape):
-                    raise RuntimeError("rank %d published buffers of a different shape" % p)
+                if tuple(peers[p][0].shape) != tuple(y.shape):
+                    raise RuntimeError("rank %d published shards of a different shape" % p)
         self._ce = {"ring": ring, "peers": peers, "side": torch.cuda.Stream(device=y.device),
-                    "push": {p: torch.cuda.Stream(device=y.device) for p in peers},
-                    "flag": torch.zeros(1, device=y.device), "ready": None, "shape": tuple(y.shape)}
-        signal = os.environ.get("MIGAN_CE_SIGNAL", "memops")
-        if signal == "memops":
-            from . import _abi
-            if not _abi.load().b200_stream_memops_available():
-                signal = "nccl"
-        votes = [None] * self.world_size
-        dist.all_gather_object(votes, signal, group=self.group)
-        signal = "memops" if all(v == "memops" for v in votes) else "nccl"      # every rank must use the same protocol
-        self._ce["signal"] = signal
-        if signal == "memops":
-            # arrival table: arrive[q] = (last step + 1) whose rows from rank q have landed in this rank's ring
-            arrive = torch.zeros(self.world_size, dtype=torch.int32, device=y.device)
-            stage = torch.zeros(self.world_size, dtype=torch.int32, device=y.device)    # per-destination source word of the 4-byte copy
-            tables = [None] * self.world_size
-            dist.all_gather_object(tables, reduce_tensor(arrive), group=self.group)
-            self._ce["arrive"] = arrive
-            self._ce["stage"] = stage
-            self._ce["peer_arrive"] = {p: tables[p][0](*tables[p][1]) for p in peers}
-            torch.cuda.synchronize(y.device)
-            dist.barrier(group=self.group)              # every table is zeroed and mapped before the first signal is sent
+                    "flag": torch.zeros(1, device=y.device), "ready": {}, "shape": tuple(y.shape)}
 
     def _forward_ce(self, y: torch.Tensor) -> GatherHandle:
-        """Push form: this rank writes its rows into slot t % RING of EVERY rank's gathered ring (posted peer-to-peer writes,
-        one stream per peer so several copy engines / NVLink ports work at once), then joins the 8-byte all-reduce.  Its
-        completion on a rank means every rank's rows have landed there.  Slot t % RING was last handed out at step t - RING and,
-        by the lifetime rule of `forward_async`, is no longer in use once its owner has CALLED forward_async(t - 1) -- which is
-        what the completed ready signal of step t - 1 certifies for every rank."""
         ce, t, n = self._ce, self._step, y.shape[0]
-        if ce["signal"] == "memops":
-            return self._forward_ce_memops(y)
         slot = t % self.RING
         cur = torch.cuda.current_stream(y.device)
+        old = ce["ready"].pop(t - self.RING + 1, None)
+        if old is not None:
+            old.wait()                                # slot's previous content (step t - RING) has been pulled by every peer
+        ce["ring"][slot].copy_(y, non_blocking=True)
+        out = torch.empty((self.world_size * n,) + tuple(y.shape[1:]), dtype=y.dtype, device=y.device)
         ev = torch.cuda.Event()
         ev.record(cur)
         side = ce["side"]
-        rows = slice(self.rank * n, (self.rank + 1) * n)
         with torch.cuda.stream(side):
             side.wait_event(ev)
-            if ce["ready"] is not None:
-                ce["ready"].wait()                    # step t-1's signal: every rank is past its use of this slot
-            base = torch.cuda.Event()
-            base.record(side)
-            ce["ring"][slot][rows].copy_(y, non_blocking=True)
-            for k in range(1, self.world_size):       # staggered: at step k every rank writes to a different destination
-                p = (self.rank + k) % self.world_size
-                bufs = ce["peers"][p]
-                st = ce["push"][p]
-                st.wait_event(base)
-                with torch.cuda.stream(st):
-                    bufs[slot][rows].copy_(y, non_blocking=True)      # peer-to-peer write, copy engine
-                    done_p = torch.cuda.Event()
-                    done_p.record(st)
-                side.wait_event(done_p)
-            ready = dist.all_reduce(ce["flag"], group=self.group, async_op=True)   # "my rows are in every rank's slot"
-        y.record_stream(side)
-        for st in ce["push"].values():
-            y.record_stream(st)
-        ce["ready"] = ready
-        return GatherHandle(ce["ring"][slot], ready, y)
-
-    def _forward_ce_memops(self, y: torch.Tensor) -> GatherHandle:
-        """Push form with no collective kernel.  Per destination q, on its own stream: wait until q's rows of step t-1 have
-        landed HERE (arrive[q] >= t: q has then passed its forward_async(t-1), i.e. is done with the slot about to be
-        overwritten -- the lifetime rule of `forward_async`), copy this rank's rows into slot t % RING of q's ring, then copy
-        the step counter t+1 into q's arrival table.  The gathered tensor is complete here when arrive[q] >= t+1 for every q;
-        those waits run on a side stream, the consumer waits for one event."""
-        from . import _abi
-        lib = _abi.load()
-        ce, t, n = self._ce, self._step, y.shape[0]
-        slot = t % self.RING
-        cur = torch.cuda.current_stream(y.device)
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        side = ce["side"]
-        rows = slice(self.rank * n, (self.rank + 1) * n)
-        arrive, stage = ce["arrive"], ce["stage"]
-        word = arrive.element_size()
-        tv, tn = t & 0xFFFFFFFF, (t + 1) & 0xFFFFFFFF
-        with torch.cuda.device(y.device):
-            for k in range(1, self.world_size):       # staggered: at step k every rank writes to a different destination
-                p = (self.rank + k) % self.world_size
-                st = ce["push"][p]
-                st.wait_event(ev)
-                _abi.check(lib.b200_stream_wait_value32(st.cuda_stream, arrive.data_ptr() + p * word, tv))
-                with torch.cuda.stream(st):
-                    ce["peers"][p][slot][rows].copy_(y, non_blocking=True)                       # peer-to-peer write, copy engine
-                _abi.check(lib.b200_stream_write_value32(st.cuda_stream, stage.data_ptr() + p * word, tn))
-                with torch.cuda.stream(st):
-                    ce["peer_arrive"][p][self.rank:self.rank + 1].copy_(stage[p:p + 1], non_blocking=True)   # 4 bytes: "my rows of step t are in"
-                y.record_stream(st)
-            with torch.cuda.stream(side):
-                side.wait_event(ev)
-                ce["ring"][slot][rows].copy_(y, non_blocking=True)
-                for p in ce["peers"]:
-                    _abi.check(lib.b200_stream_wait_value32(side.cuda_stream, arrive.data_ptr() + p * word, tn))
-                done = torch.cuda.Event()
-                done.record(side)
-            y.record_stream(side)
-        return GatherHandle(ce["ring"][slot], None, y, done)
+            ready = dist.all_reduce(ce["flag"], group=self.group, async_op=True)   # "every rank's y(t) is in its ring"
+            ready.wait()                              # the side stream (not the host) waits for it
+            for p, bufs in ce["peers"].items():
+                out[p * n:(p + 1) * n].copy_(bufs[slot], non_blocking=True)         # peer-to-peer read, copy engine
+            out[self.rank * n:(self.rank + 1) * n].copy_(ce["ring"][slot], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(side)
+        out.record_stream(side)
+        ce["ready"][t] = ready
+        return GatherHandle(out, None, y, done)
 
     def forward_async(self, x_local: torch.Tensor) -> GatherHandle:
         y = self.model(x_local)
         if self.world_size == 1:
             return GatherHandle(y, None, y)
         mode = self.gather
-        if mode in ("auto", "ce") and y.is_cuda:
+        if mode == "ce" and y.is_cuda:
             if self._ce is None or self._ce["shape"] != tuple(y.shape):
                 try:
                     self._setup_ce(y)
                 except Exception:
-                    if mode == "ce":
+                    if not self._fallback_ok:
                         raise
                     self.gather = mode = "nccl"       # e.g. no peer access between the devices
             if mode != "nccl":
@@ -256,9 +193,8 @@ class ShardedGenerator:
         return GatherHandle(out, work, y)
 
     def forward(self, x_local: torch.Tensor) -> torch.Tensor:
-        """Every rank passes its shard (equal sizes) and receives all outputs, rank-major (a tensor the caller owns)."""
-        out = self.forward_async(x_local).wait()
-        return out.clone() if self._ce is not None else out
+        """Every rank passes its shard (equal sizes) and receives all outputs, rank-major."""
+        return self.forward_async(x_local).wait()
 
     def forward_global(self, x_global: torch.Tensor) -> torch.Tensor:
         """Every rank passes the same global batch (size divisible by the world size)."""
@@ -288,8 +224,6 @@ class ShardedGenerator:
             ev_in = torch.cuda.Event()
             ev_in.record(hs["h2d"])
         cur.wait_event(ev_in)
-        if k >= 2 and hs.get("d2h_done", {}).get(k - 2) is not None:
-            cur.wait_event(hs["d2h_done"].pop(k - 2))    # ring lifetime: the copy-out of step k-2 precedes this step's ready signal
         h = self.forward_async(hs["x"][slot])
         g = h.wait()
         ev_c = torch.cuda.Event()
@@ -299,9 +233,6 @@ class ShardedGenerator:
         with torch.cuda.stream(hs["d2h"]):
             hs["d2h"].wait_event(ev_c)
             out_host_local.copy_(g[self.rank * n:(self.rank + 1) * n], non_blocking=True)
-            ev_o = torch.cuda.Event()
-            ev_o.record(hs["d2h"])
-        hs.setdefault("d2h_done", {})[k] = ev_o
         g.record_stream(hs["d2h"])
         hs["k"] = k + 1
 
@@ -312,7 +243,6 @@ class ShardedGenerator:
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
             self._ce["peers"].clear()
-            self._ce.get("peer_arrive", {}).clear()
             dist.barrier(group=self.group)
             self._ce = None
 

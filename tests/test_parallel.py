@@ -67,3 +67,26 @@ def test_sharded_generator_gloo_world2(tmp_path):
     for r in range(world):
         ok, mm = open(tmp_path / ("rank%d.ok" % r)).read().split()
         assert ok == "1" and mm == "1"
+
+
+def test_gather_policy_follows_measured_world_sizes():
+    """'auto' = copy engines at 2 GPUs, NCCL all-gather above (profiles/r02_scale_variants.md); configure_overlap sets the
+    matching SM reservation / channel count without overriding the caller's environment."""
+    assert parallel.resolve_gather("auto", 2) == "ce" and parallel.resolve_gather("auto", 8) == "nccl"
+    assert parallel.resolve_gather("auto", 4) == "nccl" and parallel.resolve_gather("ce", 8) == "ce"
+    keys = ("MIGAN_TC_RESERVE_SMS", "NCCL_MAX_NCHANNELS", "NCCL_MIN_NCHANNELS")
+    saved = {k: os.environ.pop(k, None) for k in keys}
+    try:
+        parallel.configure_overlap(world_size=2)
+        assert os.environ["MIGAN_TC_RESERVE_SMS"] == "0" and "NCCL_MAX_NCHANNELS" not in os.environ
+        del os.environ["MIGAN_TC_RESERVE_SMS"]
+        parallel.configure_overlap(world_size=8)
+        assert os.environ["MIGAN_TC_RESERVE_SMS"] == "8" and os.environ["NCCL_MAX_NCHANNELS"] == "8"
+        os.environ["MIGAN_TC_RESERVE_SMS"] = "3"
+        parallel.configure_overlap(world_size=8)
+        assert os.environ["MIGAN_TC_RESERVE_SMS"] == "3"
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+            if saved[k] is not None:
+                os.environ[k] = saved[k]

@@ -16,7 +16,7 @@ from migan_b200 import parallel, synthetic  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    mode = sys.argv[1] if len(sys.argv) > 1 else "ce"
+    mode = sys.argv[1] if len(sys.argv) > 1 else "auto"
     parallel.configure_overlap(gather=mode)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -50,9 +50,7 @@ def main():
     t = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("multi_gpu_check gather=%s (effective %s, signal %s) world=%d: %s" % (
-            mode, sg.gather if sg._ce is None else "ce", "-" if sg._ce is None else sg._ce["signal"], world,
-            "OK" if t.item() == 1.0 else "MISMATCH"), flush=True)
+        print("multi_gpu_check gather=%s (effective %s) world=%d: %s" % (mode, sg.gather if sg._ce is None else "ce", world, "OK" if t.item() == 1.0 else "MISMATCH"), flush=True)
     sg.close()
     dist.barrier()
     dist.destroy_process_group()
