@@ -12,6 +12,11 @@ timeout 200 python tools/latency.py --res 512 --out gpurun_out/r02_latency_512.j
 timeout 200 python tools/latency.py --res 256 --out gpurun_out/r02_latency_256.json > gpurun_out/r02_latency_256.log 2>&1
 # ncu: every launch of one forward (cold-cache, serialised: compare SHARES) ...
 ncu --metrics gpu__time_duration.sum --clock-control none -s 51 -c 51 --csv --log-file gpurun_out/r02_ncu_launch_list_migan512_bs32.csv python tools/ncu_target.py > /dev/null 2>&1
+if [ -n "$QUICK" ]; then   # QUICK=1: bench lines, latency and the launch list only (the full captures take ~5 GPU-minutes)
+  nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/r02_smi_after.csv
+  ls -la gpurun_out | tail -20
+  exit 0
+fi
 # ... and full captures per kernel class, second forward, 32 images
 timeout 500 $NCU -k regex:sepconv_tc -s 32 -c 5 -f -o gpurun_out/r02_ncu_tc_enc python tools/ncu_target.py > gpurun_out/ncu_a.log 2>&1
 timeout 600 $NCU -k regex:sepconv_tc -s 56 -c 8 -f -o gpurun_out/r02_ncu_tc_syn python tools/ncu_target.py > gpurun_out/ncu_b.log 2>&1
