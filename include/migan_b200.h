@@ -141,6 +141,12 @@ int b200_pipeline_preprocess(const uint8_t* image_chw, const uint8_t* mask_hw, i
 int b200_pipeline_postprocess(const float* y_nchw, uint8_t* image_chw, const uint8_t* mask_hw, int H, int W, const int* box4_host,
                               int resolution, const float* k25_host, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Training snapshot -> inference filter, scripts/export_inference_model.py:18-27 (`get_source_w`): out[cout][fan] =
+ * v * rsqrt(sum_fan v^2 + 1e-8) with v = (w_0 + ... + w_{k-1}) / sqrt(k) for a re-parameterised layer (k tensors) or v = w_0
+ * (k = 1).  w_dev: HOST array of k DEVICE pointers to [cout][fan] fp32 tensors (fan = cin/groups * kh * kw); out: device.
+ * Agrees with the reference's CPU result to a few ulp (the sum of squares is accumulated in fp64). */
+int b200_reparam_filter(const float* const* w_dev, int k, int cout, int64_t fan, float* out, void* stream);
+
 /* Stream memory operations for multi-GPU signalling (mi-gan_b200/parallel.py): the stream waits until the 32-bit word at a
  * DEVICE address reaches `value` (cyclic comparison (int32)(*addr - value) >= 0), or writes `value` to it, in stream order.
  * Executed by the stream's front end: no kernel, no SM.  b200_stream_memops_available() is 1 when the driver offers them. */

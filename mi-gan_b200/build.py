@@ -18,7 +18,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libmigan_b200.so")
 STAMP = os.path.join(LIBDIR, "libmigan_b200.stamp")
 
-SOURCES = ["elementwise.cu", "gemm_simt.cu", "ops.cu", "sepconv_tc.cu", "migan_abi.cu", "comodgan_abi.cu", "prepost.cu", "pipeline.cu"]
+SOURCES = ["elementwise.cu", "gemm_simt.cu", "ops.cu", "sepconv_tc.cu", "migan_abi.cu", "comodgan_abi.cu", "prepost.cu", "pipeline.cu", "reparam.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

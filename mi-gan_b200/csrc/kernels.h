@@ -82,4 +82,8 @@ int launch_pipeline_preprocess(const uint8_t* image, const uint8_t* mask, int H,
 int launch_pipeline_postprocess(const float* y, uint8_t* image, const uint8_t* mask, int H, int W, const int* box, int res,
                                 const float* k25_host, void* scratch, cudaStream_t s);
 
+
+// ---- training snapshot -> inference filters (reparam.cu): scripts/export_inference_model.py:18-27 ------
+int launch_reparam_filter(const float* const* w_dev, int k, int cout, int64_t fan, float* out, cudaStream_t s);
+
 }  // namespace migan

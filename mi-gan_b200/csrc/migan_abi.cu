@@ -1259,6 +1259,17 @@ int b200_stream_write_value32(void* stream, void* addr, uint32_t value) {
     return MIGAN_OK;
 }
 
+// ---- training snapshot -> inference filters (scripts/export_inference_model.py:18-27), kernel in reparam.cu ----
+int b200_reparam_filter(const float* const* w_dev, int k, int cout, int64_t fan, float* out, void* stream) {
+    if (!w_dev || !out) return fail(MIGAN_ERR_INVALID, "reparam_filter: null argument");
+    if (k < 1 || k > 16) return fail(MIGAN_ERR_INVALID, "reparam_filter: %d tensors (1 .. 16 supported)", k);
+    if (cout < 1 || fan < 1) return fail(MIGAN_ERR_INVALID, "reparam_filter: bad shape %d x %lld", cout, (long long)fan);
+    for (int j = 0; j < k; ++j)
+        if (!w_dev[j]) return fail(MIGAN_ERR_INVALID, "reparam_filter: tensor %d is null", j);
+    CUDA_TRY((cudaError_t)migan::launch_reparam_filter(w_dev, k, cout, fan, out, static_cast<cudaStream_t>(stream)));
+    return MIGAN_OK;
+}
+
 int b200_enable_peer_access(int peer_device) {
     const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
     if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return MIGAN_OK; }

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "mi-gan_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libcomod_emul.so")
-SRCS = ["comodgan_abi.cu", "prepost.cu", "pipeline.cu", "comod_kernels.cuh", os.path.join("..", "..", "include", "comodgan_b200.h")]
+SRCS = ["comodgan_abi.cu", "prepost.cu", "pipeline.cu", "reparam.cu", "comod_kernels.cuh", os.path.join("..", "..", "include", "comodgan_b200.h")]
 
 
 def _hash() -> str:
@@ -32,7 +32,7 @@ def build() -> str:
     if os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == _hash():
         return LIB
     cmd = ["g++", "-O2", "-fopenmp", "-shared", "-fPIC", "-std=c++17", "-DMIGAN_EMULATE", "-x", "c++",
-           "comodgan_abi.cu", "prepost.cu", "pipeline.cu", "-o", LIB]
+           "comodgan_abi.cu", "prepost.cu", "pipeline.cu", "reparam.cu", "-o", LIB]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("emulation build failed:\n" + proc.stderr[-4000:])

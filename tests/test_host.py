@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import sys
 
 import pytest
 import torch
@@ -216,3 +217,71 @@ def test_resolutions_above_512_are_rejected_up_front(lib):
     assert lib.migan_create(1024, 0, ctypes.byref(h)) == 1 and b"64 channels" in lib.migan_last_error()
     assert lib.migan_create(1024, -1, ctypes.byref(h)) == 0
     lib.migan_destroy(h)
+
+
+def _emul_reparam(ws):
+    """The export kernel's functor compiled for the host (tests/emul), on numpy copies of the tensors."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+    import build_emul
+    emul = ctypes.CDLL(build_emul.build())
+    emul.b200_reparam_filter.restype = ctypes.c_int
+    emul.b200_reparam_filter.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    arrs = [np.ascontiguousarray(w.detach().numpy(), dtype=np.float32) for w in ws]
+    out = np.empty_like(arrs[0])
+    ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    assert emul.b200_reparam_filter(ctypes.cast(ptrs, ctypes.c_void_p), len(arrs), arrs[0].shape[0], arrs[0][0].size,
+                                    out.ctypes.data_as(ctypes.c_void_p), None) == 0
+    return torch.from_numpy(out)
+
+
+def test_export_kernel_matches_oracle_in_emulation():
+    """csrc/reparam.cu (host-emulation build) against oracle/export_oracle.merged_filter: depthwise 3x3, 1x1 and k = 1 / 9 tensors.
+    Bar: relative error < 1e-6 of the filter's largest tap (the sum of squares is accumulated in fp64 instead of torch's fp32 tree)."""
+    from oracle import export_oracle as E
+    g = torch.Generator().manual_seed(3)
+    for shape, k in (((64, 1, 3, 3), 9), ((128, 64, 1, 1), 9), ((3, 512, 1, 1), 1), ((512, 512, 1, 1), 4), ((64, 4, 1, 1), 1)):
+        ws = [torch.randn(shape, generator=g) * (0.5 + i) for i in range(k)]
+        got, want = _emul_reparam(ws), E.merged_filter(ws)
+        assert got.shape == want.shape
+        err = (got - want).abs().amax(dim=(1, 2, 3)) / want.abs().amax(dim=(1, 2, 3))
+        assert float(err.max()) < 1e-6, (shape, k, float(err.max()))
+        assert torch.allclose(got.flatten(1).square().sum(1), torch.ones(shape[0]), atol=1e-5)   # unit L2 filters
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/lib/model_zoo"), reason="reference checkout not present (GPU box)")
+def test_export_matches_reference_copy_weights(monkeypatch):
+    """oracle/export_oracle.merged_filter == the reference's `get_source_w` (through its effect: `copy_weights` into the
+    reference's inference Generator), and the export kernel (emulation) reproduces every filter of that state_dict.
+    Build container only."""
+    import importlib
+    import warnings
+    from oracle import export_oracle as E
+    monkeypatch.syspath_prepend("/root/reference")
+    warnings.filterwarnings("ignore")
+    M = importlib.import_module("lib.model_zoo.migan")
+    ref_inf = importlib.import_module("lib.model_zoo.migan_inference")
+    exp = importlib.import_module("scripts.export_inference_model")
+    R = 64
+    torch.manual_seed(1)
+    src = M.Generator(M.Encoder(resolution=R, ic_n=4, depthwise=True, reparametrize=True, num_reparam_tensors=9),
+                      M.Synthesis(resolution=R, depthwise=True, reparametrize=True, num_reparam_tensors=9)).eval()
+    ref = ref_inf.Generator(resolution=R).eval()
+    exp.copy_weights(src, ref, resolution=R)
+    sd = ref.state_dict()
+    checked = 0
+    for side in ("encoder", "synthesis"):
+        for res in (4, 8, 16, 32, 64):
+            blk = getattr(getattr(src, side), "b%d" % res)
+            convs = [("conv1.conv1", blk.conv1.conv1), ("conv1.conv2", blk.conv1.conv2), ("conv2.conv1", blk.conv2.conv1), ("conv2.conv2", blk.conv2.conv2)]
+            head = "fromrgb" if side == "encoder" else "torgb"
+            if "%s.b%d.%s.weight" % (side, res, head) in sd:
+                convs.append((head, getattr(blk, head)))
+            for name, conv in convs:
+                ws = [getattr(conv, "w%d" % i).detach() for i in range(conv.num_reparam_tensors)] if conv.reparametrize else [conv.weight.detach()]
+                want = sd["%s.b%d.%s.weight" % (side, res, name)]
+                assert torch.equal(E.merged_filter(ws), want), (side, res, name)           # the oracle IS the reference expression
+                got = _emul_reparam(ws)
+                assert float(((got - want).abs().amax(dim=(1, 2, 3)) / want.abs().amax(dim=(1, 2, 3))).max()) < 1e-6
+                checked += 1
+    assert checked == 46      # 5 levels x 2 sides x 4 convolutions + 1 fromrgb + 5 torgb
