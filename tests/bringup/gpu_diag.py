@@ -1,5 +1,5 @@
 """GPU bring-up diagnostics: per-stage error vs the oracle and a quick timing.
-    python tools/gpu_diag.py --path simt --res 64 --n 2
+    python tests/bringup/gpu_diag.py --path simt --res 64 --n 2
 Test/debug tooling (imports the oracle as the checker)."""
 import argparse
 import os
@@ -8,7 +8,7 @@ import time
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import migan_b200  # noqa: E402
 from oracle import migan_oracle as O  # noqa: E402
 
