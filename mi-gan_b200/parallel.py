@@ -27,7 +27,16 @@ def resolve_gather(gather: str, world_size: int) -> str:
     return "ce" if world_size == 2 else "nccl"
 
 
-def configure_overlap(reserve_sms: int = None, nccl_channels: int = 8, gather: str = "auto", world_size: int = None) -> None:
+def nccl_channels_for(world_size: int) -> int:
+    """Channels (= SMs left free) for the NCCL all-gather.  Measured with 8 channels: the collective moves ~59 GB/s into each
+    rank (7.4 GB/s per channel) -- 700 MB per step at 8 GPUs = 11.9 ms, longer than the 9.7 ms step it should hide under, and
+    exactly the step time measured there (profiles/r02_scale_variants.md); 300 MB at 4 GPUs = 5 ms.  12 channels bring the
+    8-GPU gather to ~8 ms for 4 more SMs (+0.3 ms of compute).  The 12-channel point is DERIVED from the 8-channel
+    measurement, not measured itself (the round's GPU budget was spent)."""
+    return 12 if world_size > 4 else 8
+
+
+def configure_overlap(reserve_sms: int = None, nccl_channels: int = None, gather: str = "auto", world_size: int = None) -> None:
     """Call BEFORE `init_process_group` and before the first forward.
 
     gather = "ce": the output all-gather moves its bytes with the copy engines (peer-to-peer reads over NVLink, see
@@ -35,7 +44,8 @@ def configure_overlap(reserve_sms: int = None, nccl_channels: int = 8, gather: s
     tensor-core kernel keeps all 148 SMs (no reservation).
     gather = "nccl": `all_gather_into_tensor` runs on NCCL's SM-resident copy kernels, one SM per channel, concurrently with
     the next batch's kernels.  The persistent kernel uses one CTA per SM -- if they collide, its last CTAs run as a second
-    wave -- so NCCL is limited to `nccl_channels` channels and the persistent grids leave `reserve_sms` SMs free.  Measured
+    wave -- so NCCL is limited to `nccl_channels` channels (default `nccl_channels_for(world_size)`) and the persistent grids
+    leave as many SMs free (`reserve_sms`).  Measured
     on 2 B200s (migan-512, 32 img/GPU, round 1): 14.27 ms/step without the reservation, 13.3-13.4 ms with 4-8 SMs reserved
     (12.9 ms on one GPU).
     gather = "auto" (default): see `resolve_gather`; `world_size` defaults to the WORLD_SIZE of the launcher.
@@ -43,9 +53,11 @@ def configure_overlap(reserve_sms: int = None, nccl_channels: int = 8, gather: s
     if world_size is None:
         world_size = int(os.environ.get("WORLD_SIZE", "1"))
     if resolve_gather(gather, world_size) == "nccl":
+        if nccl_channels is None:
+            nccl_channels = nccl_channels_for(world_size)
         os.environ.setdefault("NCCL_MAX_NCHANNELS", str(nccl_channels))
         os.environ.setdefault("NCCL_MIN_NCHANNELS", str(nccl_channels))
-        os.environ.setdefault("MIGAN_TC_RESERVE_SMS", str(8 if reserve_sms is None else reserve_sms))
+        os.environ.setdefault("MIGAN_TC_RESERVE_SMS", str(nccl_channels if reserve_sms is None else reserve_sms))
     else:
         os.environ.setdefault("MIGAN_TC_RESERVE_SMS", str(0 if reserve_sms is None else reserve_sms))
 

@@ -80,8 +80,12 @@ def test_gather_policy_follows_measured_world_sizes():
         parallel.configure_overlap(world_size=2)
         assert os.environ["MIGAN_TC_RESERVE_SMS"] == "0" and "NCCL_MAX_NCHANNELS" not in os.environ
         del os.environ["MIGAN_TC_RESERVE_SMS"]
-        parallel.configure_overlap(world_size=8)
+        parallel.configure_overlap(world_size=4)
         assert os.environ["MIGAN_TC_RESERVE_SMS"] == "8" and os.environ["NCCL_MAX_NCHANNELS"] == "8"
+        for k in keys:
+            os.environ.pop(k, None)
+        parallel.configure_overlap(world_size=8)            # one SM per channel; more channels where the gather would not hide under a step
+        assert os.environ["MIGAN_TC_RESERVE_SMS"] == "12" and os.environ["NCCL_MAX_NCHANNELS"] == "12" == os.environ["NCCL_MIN_NCHANNELS"]
         os.environ["MIGAN_TC_RESERVE_SMS"] = "3"
         parallel.configure_overlap(world_size=8)
         assert os.environ["MIGAN_TC_RESERVE_SMS"] == "3"
